@@ -1,0 +1,121 @@
+"""The oracle (oracle/geometry.py) against the reference's own outputs (tests/golden/*.npz,
+made by tests/golden/make_golden.py from the unmodified reference)."""
+import numpy as np
+import pytest
+
+from oracle import geometry as og
+
+
+def _frames(g):
+    ids = list(g["image_ids"])
+    return [ids.index(v) for v in g["valid_ids"]]
+
+
+def test_invalid_poses_are_dropped(golden_scannet):
+    g = golden_scannet
+    valid = [i for i, E in zip(g["image_ids"], g["c2w"]) if og.pose_is_valid(E)]
+    assert valid == list(g["valid_ids"])
+    assert len(valid) < len(g["image_ids"])          # the fixture plants -inf poses
+
+
+def test_projection_and_visibility_match_reference(golden_scannet):
+    g = golden_scannet
+    H, W = g["image_hw"]
+    pts = g["points"].astype(np.float64)
+    for k, f in enumerate(_frames(g)):
+        E = og.aligned_pose(g["axis_align"], g["c2w"][f])
+        np.testing.assert_array_equal(E, g["ref_E_aligned"][k])
+        xy, z, m = og.frame_visibility(pts, g["K"], E, g["depth"][f], H, W)
+        # same NumPy/BLAS build as the generator -> bit-identical floats; the
+        # judged bar is 1e-5 relative for floats and exact for masks.
+        np.testing.assert_allclose(xy, g["ref_xy"][k], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(z, g["ref_z"][k], rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(m, g["ref_mask"][k])
+
+
+def test_mask_bit_packing_roundtrip(golden_scannet):
+    m = golden_scannet["ref_mask"][0]
+    w = og.pack_mask_bits(m)
+    assert w.dtype == np.uint32 and w.shape[0] == (m.shape[0] + 31) // 32
+    np.testing.assert_array_equal(og.unpack_mask_bits(w, m.shape[0]), m)
+    assert int(sum(bin(int(x)).count("1") for x in w)) == int(m.sum())
+
+
+def test_visibility_tables_match_mvi(golden_scannet):
+    g = golden_scannet
+    off = g["ref_i2p_off"]
+    for k in range(len(g["valid_ids"])):
+        np.testing.assert_array_equal(np.where(g["ref_mask"][k])[0], g["ref_i2p_flat"][off[k]:off[k + 1]])
+    np.testing.assert_array_equal(g["ref_mask"].sum(0), g["ref_p2i_cnt"])
+
+
+def test_pair_relations_match_cfr(golden_scannet):
+    g = golden_scannet
+    valid = list(g["valid_ids"])
+    for (a, b), vals in zip(g["ref_pair_ids"], g["ref_pair_vals"]):
+        i, j = valid.index(a), valid.index(b)
+        assert i < j
+        r = og.pair_relations(g["ref_E_aligned"][i], g["ref_E_aligned"][j], g["ref_mask"][i], g["ref_mask"][j])
+        got = np.array([r["overlap"], r["distance"], r["yaw"], r["pitch"]])
+        np.testing.assert_allclose(got, vals, rtol=1e-13, atol=1e-13, equal_nan=True)
+    n = len(valid)
+    assert len(g["ref_pair_ids"]) == n * (n - 1) // 2
+
+
+def test_point_annotation_matches_reference(golden_scannet):
+    g = golden_scannet
+    H, W = g["image_hw"]
+    fr = _frames(g)
+    for row in g["ref_spot"]:
+        k, p = int(row[0]), int(row[1])
+        f = fr[k]
+        a = og.annotate_point(g["points"][p].astype(np.float64), g["K"], g["ref_E_aligned"][k], g["depth"][f], H, W)
+        assert a is not None
+        np.testing.assert_allclose([a["u"], a["v"], a["z"]], row[2:5], rtol=1e-12)
+        assert [a["x_permille"], a["y_permille"], a["depth_mm"], a["pix"][0], a["pix"][1]] == [int(v) for v in row[5:10]]
+
+
+def test_common_points_is_mask_and(golden_scannet):
+    g = golden_scannet
+    a, b = g["ref_mask"][0], g["ref_mask"][1]
+    np.testing.assert_array_equal(og.common_visible_points(np.where(a)[0], np.where(b)[0]), np.where(a & b)[0])
+
+
+def test_object_counts(golden_scannet):
+    g = golden_scannet
+    inst, nobj = g["instance_ids"], int(g["num_objects"])
+    m = g["ref_mask"][2]
+    c = og.object_visible_counts(m, inst, nobj)
+    for o in range(nobj):
+        assert c[o] == len(set(np.where(m)[0].tolist()) & set(np.where(inst == o + 1)[0].tolist()))
+
+
+def test_tapvid_matches_reference(golden_tapvid):
+    g = golden_tapvid
+    H, W = g["image_hw"]
+    world = og.tracks_to_world(g["tracks_xyz"], g["w2c"])
+    np.testing.assert_allclose(world, g["ref_world"], rtol=1e-13, atol=1e-13)
+    T, N, _ = g["tracks_xyz"].shape
+    for t in range(T):
+        for n in range(N):
+            r = og.track_project_point(g["tracks_xyz"][t, n], g["fxfycxcy"], H, W)
+            if r is None:
+                assert np.isnan(g["ref_proj"][t, n, 0])
+            else:
+                np.testing.assert_allclose(r, g["ref_proj"][t, n], rtol=1e-14)
+
+
+def test_live_reference_agrees_when_present(golden_scannet):
+    """Re-run the real reference function when /root/reference exists (build container)."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference checkout not present on this machine")
+    ref = ref_shim.import_reference()
+    g = golden_scannet
+    pts = og.homogenize(g["points"].astype(np.float64))
+    E = g["ref_E_aligned"][0]
+    with np.errstate(all="ignore"):
+        xy_r, z_r = ref.info_handler.project_points(pts, g["K"], E)
+        xy_o, z_o = og.project_points(pts, g["K"], E)
+    np.testing.assert_array_equal(np.asarray(xy_r), np.asarray(xy_o))
+    np.testing.assert_array_equal(z_r, z_o)
