@@ -1,0 +1,235 @@
+// Device-side building blocks of the MultiSPA geometry hot path (sm_100a).
+//
+// Arithmetic contract.  Everything that decides an integer (mask bit, pixel index, per-mille value) is
+// evaluated in float64 with explicitly rounded operations in the order the reference's NumPy/BLAS code
+// uses: np.linalg.inv(E) once per frame, cam = Einv @ P^T as a k-sequential FMA chain (what OpenBLAS
+// dgemm does for the 4-term dot products; verified bit-for-bit against numpy in this repo's tests),
+// img = K @ cam likewise, then a true IEEE division (info_handler.py:57-69).  Explicit __fma_rn/__dmul_rn
+// keep nvcc from re-associating or contracting differently.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msp {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  // make the init visible to the async proxy before a bulk copy signals the barrier
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy; bytes and both addresses must be multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint16_t ldg_u16_nc(const uint16_t* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------------
+// camera model
+// ------------------------------------------------------------------------------------------------
+struct Intrinsics {  // rows 0..2 of the reference's 4x4 K (info_handler.py:11, update_info_file_with_images.py:55-69)
+  double k[12];
+};
+struct ImageGeom {
+  double img_w, img_h;  // float64 copies of the integer sizes (compared against u, v: IH:342-343)
+  double sx, sy;        // depth_w / image_w, depth_h / image_h (IH:356-357)
+  double depth_scale;   // IH:368
+  int32_t depth_w, depth_h;
+  int32_t image_w, image_h;
+};
+
+// cam = (w2c rows 0..2) . [x y z 1], k-sequential FMA chain (IH:60)
+__device__ __forceinline__ double row_dot_h(const double* __restrict__ r, double x, double y, double z) {
+  return __dadd_rn(__fma_rn(r[2], z, __fma_rn(r[1], y, __dmul_rn(r[0], x))), r[3]);
+}
+__device__ __forceinline__ double row_dot4(const double* __restrict__ r, double a, double b, double c, double d) {
+  return __fma_rn(r[3], d, __fma_rn(r[2], c, __fma_rn(r[1], b, __dmul_rn(r[0], a))));
+}
+
+struct Proj {
+  double u, v, z;
+};
+
+// Exact projection of one point.  STD = the w2c bottom row is [0,0,0,1] and K is [fx 0 cx 0; 0 fy cy 0; 0 0 1 0],
+// for which the zero terms of the BLAS dot products vanish exactly and cam.w == 1.
+template <bool STD>
+__device__ __forceinline__ Proj project_exact(const double* __restrict__ w /*16 or 12*/, const Intrinsics& K, double x,
+                                              double y, double z) {
+  Proj p;
+  const double X = row_dot_h(w + 0, x, y, z);
+  const double Y = row_dot_h(w + 4, x, y, z);
+  const double Z = row_dot_h(w + 8, x, y, z);
+  p.z = Z;  // points_depth = camera_coords[2] (IH:63)
+  if (STD) {
+    const double i0 = __fma_rn(K.k[2], Z, __dmul_rn(K.k[0], X));
+    const double i1 = __fma_rn(K.k[6], Z, __dmul_rn(K.k[5], Y));
+    p.u = __ddiv_rn(i0, Z);
+    p.v = __ddiv_rn(i1, Z);
+  } else {
+    const double W = row_dot_h(w + 12, x, y, z);
+    const double i0 = row_dot4(K.k + 0, X, Y, Z, W);
+    const double i1 = row_dot4(K.k + 4, X, Y, Z, W);
+    const double i2 = row_dot4(K.k + 8, X, Y, Z, W);
+    p.u = __ddiv_rn(i0, i2);
+    p.v = __ddiv_rn(i1, i2);
+  }
+  return p;
+}
+
+__device__ __forceinline__ bool in_image(const Proj& p, const ImageGeom& g) {  // IH:342-343
+  return (p.u >= 0.0) & (p.u < g.img_w) & (p.v >= 0.0) & (p.v < g.img_h);
+}
+
+// IH:359-366 for a point already known to be inside the colour image (so the products are in [0, depth_w]).
+__device__ __forceinline__ int depth_index(const Proj& p, const ImageGeom& g) {
+  int dx = __double2int_rn(__dmul_rn(p.u, g.sx));  // np.round = half-even; astype(int)
+  int dy = __double2int_rn(__dmul_rn(p.v, g.sy));
+  dx = min(max(dx, 0), g.depth_w - 1);
+  dy = min(max(dy, 0), g.depth_h - 1);
+  return dy * g.depth_w + dx;
+}
+
+// IH:368-371
+__device__ __forceinline__ bool depth_test(double z, uint16_t raw, const ImageGeom& g) {
+  const double d = __dmul_rn(static_cast<double>(raw), g.depth_scale);
+  return (z > 0.0) & (z < d);
+}
+
+template <bool STD>
+__device__ __forceinline__ bool visible_exact(const double* __restrict__ w, const Intrinsics& K, const ImageGeom& g,
+                                              const uint16_t* __restrict__ depth, double x, double y, double z,
+                                              Proj& out) {
+  out = project_exact<STD>(w, K, x, y, z);
+  bool vis = false;
+  if (in_image(out, g) && out.z > 0.0) {
+    vis = depth_test(out.z, ldg_u16_nc(depth + depth_index(out, g)), g);
+  }
+  return vis;
+}
+
+// sample integers (visual_correspondence_qa_engine_coor_2_coor.py:341-344, depth_estimation_dot_engine.py:216-218,261)
+__device__ __forceinline__ int permille(double coord, double extent) {
+  return __double2int_rn(__dmul_rn(__ddiv_rn(coord, extent), 1000.0));
+}
+__device__ __forceinline__ int depth_mm(double z) { return __double2int_rn(__dmul_rn(z, 1000.0)); }
+
+// ------------------------------------------------------------------------------------------------
+// point loads
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+struct PtTraits;
+template <>
+struct PtTraits<0> {
+  static constexpr int kBytes = 12;
+  __device__ static __forceinline__ void load(const void* base, int64_t i, double& x, double& y, double& z) {
+    const float* p = static_cast<const float*>(base) + 3 * i;
+    x = p[0], y = p[1], z = p[2];
+  }
+};
+template <>
+struct PtTraits<1> {
+  static constexpr int kBytes = 16;
+  __device__ static __forceinline__ void load(const void* base, int64_t i, double& x, double& y, double& z) {
+    const float4 q = static_cast<const float4*>(base)[i];
+    x = q.x, y = q.y, z = q.z;
+  }
+};
+template <>
+struct PtTraits<2> {
+  static constexpr int kBytes = 24;
+  __device__ static __forceinline__ void load(const void* base, int64_t i, double& x, double& y, double& z) {
+    const double* p = static_cast<const double*>(base) + 3 * i;
+    x = p[0], y = p[1], z = p[2];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// 4x4 helpers for the pose prologue
+// ------------------------------------------------------------------------------------------------
+// C = A @ B with the same k-sequential FMA chain as the BLAS call behind IH:122.
+__device__ inline void matmul4(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double acc = __dmul_rn(A[i * 4 + 0], B[0 * 4 + j]);
+      acc = __fma_rn(A[i * 4 + 1], B[1 * 4 + j], acc);
+      acc = __fma_rn(A[i * 4 + 2], B[2 * 4 + j], acc);
+      acc = __fma_rn(A[i * 4 + 3], B[3 * 4 + j], acc);
+      C[i * 4 + j] = acc;
+    }
+}
+
+// inverse by LU with partial pivoting and two triangular solves against the identity (the LAPACK gesv
+// recipe np.linalg.inv follows).  Returns false for a singular matrix.
+__device__ inline bool inverse4(const double* M, double* inv) {
+  double a[16];
+  int perm[4] = {0, 1, 2, 3};
+  for (int i = 0; i < 16; ++i) a[i] = M[i];
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    double best = fabs(a[c * 4 + c]);
+    for (int r = c + 1; r < 4; ++r) {
+      const double v = fabs(a[r * 4 + c]);
+      if (v > best) best = v, piv = r;
+    }
+    if (!(best > 0.0)) return false;
+    if (piv != c) {
+      for (int k = 0; k < 4; ++k) {
+        const double t = a[c * 4 + k];
+        a[c * 4 + k] = a[piv * 4 + k];
+        a[piv * 4 + k] = t;
+      }
+      const int t = perm[c];
+      perm[c] = perm[piv];
+      perm[piv] = t;
+    }
+    const double rp = __ddiv_rn(1.0, a[c * 4 + c]);
+    for (int r = c + 1; r < 4; ++r) {
+      const double l = __dmul_rn(a[r * 4 + c], rp);
+      a[r * 4 + c] = l;
+      for (int k = c + 1; k < 4; ++k) a[r * 4 + k] = __fma_rn(-l, a[c * 4 + k], a[r * 4 + k]);
+    }
+  }
+  for (int j = 0; j < 4; ++j) {  // solve L U x = P e_j
+    double y[4];
+    for (int i = 0; i < 4; ++i) {
+      double s = (perm[i] == j) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s = __fma_rn(-a[i * 4 + k], y[k], s);
+      y[i] = s;
+    }
+    for (int i = 3; i >= 0; --i) {
+      double s = y[i];
+      for (int k = i + 1; k < 4; ++k) s = __fma_rn(-a[i * 4 + k], inv[k * 4 + j], s);
+      inv[i * 4 + j] = __ddiv_rn(s, a[i * 4 + i]);
+    }
+  }
+  return true;
+}
+
+}  // namespace msp

@@ -1,0 +1,720 @@
+// libmsp.so — hand-written sm_100a kernels + C ABI for the MultiSPA geometry hot path.
+// Entry points and the reference lines they replace are documented in include/msp.h.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "msp.h"
+#include "msp_device.cuh"
+
+using namespace msp;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return MSP_OK;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return MSP_ELAUNCH;
+}
+#define REQUIRE(cond, msg)                                    \
+  do {                                                        \
+    if (!(cond)) return fail(MSP_EINVAL, msg);          \
+  } while (0)
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// K0: pose prologue (one thread per frame)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pose_prepare(const double* __restrict__ c2w, const double* __restrict__ axis_align, int F,
+                               double* __restrict__ E_out, double* __restrict__ w2c_out,
+                               double* __restrict__ yawpitch_out, int* __restrict__ valid_out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  double C[16], E[16], inv[16];
+  bool finite = true;
+  for (int i = 0; i < 16; ++i) {
+    C[i] = c2w[(int64_t)f * 16 + i];
+    finite &= isfinite(C[i]);  // info_handler.py:414-416
+  }
+  if (axis_align != nullptr) {
+    double A[16];
+    for (int i = 0; i < 16; ++i) A[i] = axis_align[i];
+    matmul4(A, C, E);  // info_handler.py:122
+  } else {
+    for (int i = 0; i < 16; ++i) E[i] = C[i];
+  }
+  bool ok = finite && inverse4(E, inv);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int i = 0; i < 16; ++i) {
+    E_out[(int64_t)f * 16 + i] = E[i];
+    w2c_out[(int64_t)f * 16 + i] = ok ? inv[i] : qnan;
+  }
+  // calculate_frames_relations.py:86-100 — viewing direction is the third column of the rotation block
+  const double zx = E[2], zy = E[6], zz = E[10];
+  const double kDeg = 180.0 / 3.14159265358979323846;
+  const double nrm = sqrt(__fma_rn(zz, zz, __fma_rn(zy, zy, __dmul_rn(zx, zx))));
+  yawpitch_out[(int64_t)f * 2 + 0] = atan2(zy, zx) * kDeg;
+  yawpitch_out[(int64_t)f * 2 + 1] = asin(zz / nrm) * kDeg;
+  valid_out[f] = ok ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 / K2: per-(frame, point) projection with either the depth-map visibility test (bit mask out)
+// or a z-buffer splat.  A CTA stages one tile of points in shared memory with a bulk async copy,
+// keeps each lane's points in registers as float64 and walks a chunk of frames over them.
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kWordsPerWarp = 4;                          // 32-bit mask words produced per warp per frame
+constexpr int kTilePoints = kWarps * kWordsPerWarp * 32;  // 1024
+constexpr int kFramesPerCta = 32;
+
+struct FrameLoopParams {
+  const void* pts;
+  int64_t n;
+  const double* w2c;  // (F,16)
+  int32_t F;
+  const uint16_t* depth;  // (F, dh*dw)        [visibility]
+  float* zbuf;            // (F, dh*dw)        [z-buffer]
+  int64_t depth_stride;   // dh*dw
+  uint32_t* mask;
+  int64_t mask_stride;
+  double* xy;
+  double* z;
+  Intrinsics K;
+  ImageGeom g;
+};
+
+enum { MODE_VIS = 0, MODE_ZBUF = 1 };
+
+template <int DT, bool KSTD, int MODE, bool MAT>
+__global__ void __launch_bounds__(kThreads) k_frame_loop(const FrameLoopParams p) {
+  __shared__ __align__(128) unsigned char s_pts[kTilePoints * PtTraits<DT>::kBytes];
+  __shared__ __align__(16) double s_w[kFramesPerCta * 16];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * kTilePoints;
+  const int cnt = (int)min((int64_t)kTilePoints, p.n - base);
+  const int f0 = blockIdx.y * kFramesPerCta;
+  const int nf = min(kFramesPerCta, p.F - f0);
+
+  // ---- stage the point tile: one elected thread issues the bulk copy, everybody waits on the mbarrier
+  const uint32_t bytes = (uint32_t)cnt * PtTraits<DT>::kBytes;
+  const uint32_t bulk = bytes & ~15u;
+  const unsigned char* gsrc = static_cast<const unsigned char*>(p.pts) + base * PtTraits<DT>::kBytes;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&s_bar, bulk);
+    if (bulk) bulk_g2s(s_pts, gsrc, bulk, &s_bar);
+  }
+  if (tid < (int)(bytes - bulk)) s_pts[bulk + tid] = gsrc[bulk + tid];
+  for (int i = tid; i < nf * 16; i += kThreads) s_w[i] = p.w2c[(int64_t)f0 * 16 + i];
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  double px[kWordsPerWarp], py[kWordsPerWarp], pz[kWordsPerWarp];
+  bool ok[kWordsPerWarp];
+#pragma unroll
+  for (int j = 0; j < kWordsPerWarp; ++j) {
+    const int idx = warp * (kWordsPerWarp * 32) + j * 32 + lane;
+    ok[j] = idx < cnt;
+    px[j] = py[j] = pz[j] = 0.0;
+    if (ok[j]) PtTraits<DT>::load(s_pts, idx, px[j], py[j], pz[j]);
+  }
+  const int64_t word0 = (int64_t)blockIdx.x * (kTilePoints / 32) + warp * kWordsPerWarp;
+
+  for (int fi = 0; fi < nf; ++fi) {
+    const double* w = s_w + fi * 16;
+    const int64_t f = f0 + fi;
+    const bool fstd = KSTD && (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
+    uint32_t myword = 0;
+#pragma unroll
+    for (int j = 0; j < kWordsPerWarp; ++j) {
+      Proj pr = fstd ? project_exact<true>(w, p.K, px[j], py[j], pz[j])
+                     : project_exact<false>(w, p.K, px[j], py[j], pz[j]);
+      const bool cand = ok[j] && in_image(pr, p.g) && (pr.z > 0.0);
+      if (MODE == MODE_VIS) {
+        bool vis = false;
+        if (cand) vis = depth_test(pr.z, ldg_u16_nc(p.depth + f * p.depth_stride + depth_index(pr, p.g)), p.g);
+        const uint32_t b = __ballot_sync(0xffffffffu, vis);
+        if (lane == j) myword = b;
+      } else {
+        if (cand)
+          atomicMin(reinterpret_cast<unsigned int*>(p.zbuf + f * p.depth_stride) + depth_index(pr, p.g),
+                    __float_as_uint(__double2float_rn(pr.z)));
+      }
+      if (MAT && ok[j]) {
+        const int64_t gi = f * p.n + base + warp * (kWordsPerWarp * 32) + j * 32 + lane;
+        reinterpret_cast<double2*>(p.xy)[gi] = make_double2(pr.u, pr.v);
+        p.z[gi] = pr.z;
+      }
+    }
+    if (MODE == MODE_VIS) {
+      if (lane < kWordsPerWarp && word0 + lane < p.mask_stride) p.mask[f * p.mask_stride + word0 + lane] = myword;
+    }
+  }
+}
+
+__global__ void k_fill_u32(uint32_t* __restrict__ dst, int64_t count, uint32_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = i; k < count; k += stride) dst[k] = v;
+}
+
+__global__ void k_depth_to_u16(const float* __restrict__ zbuf, int64_t count, int margin_mm, double depth_scale,
+                               uint16_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = i; k < count; k += stride) {
+    const float zf = zbuf[k];
+    uint16_t r = 0;
+    if (isfinite(zf)) {
+      double mm = floor(__ddiv_rn((double)zf, depth_scale)) + 1.0 + (double)margin_mm;
+      mm = fmin(mm, 65535.0);
+      r = (uint16_t)mm;
+    }
+    out[k] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3/K4: the per-pair stage.  One CTA per pair; each warp owns a contiguous quarter of the mask row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 128;
+constexpr int kPairWarps = kPairThreads / 32;
+
+struct PairParams {
+  const uint32_t* mask;
+  int64_t n;
+  int64_t mask_stride;
+  const int32_t* pairs;
+  int64_t P;
+  const uint32_t* sel;
+  int32_t sel_mode;
+  const void* pts;
+  const double* E;
+  const double* w2c;
+  const double* yawpitch;
+  const uint16_t* depth;
+  int64_t depth_stride;
+  Intrinsics K;
+  ImageGeom g;
+  msp_pair_record* rec;
+  uint32_t* inter_out;
+  uint32_t* uni_out;
+  double* overlap_out;
+};
+
+__device__ __forceinline__ uint32_t popc4(const uint4 v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+__device__ __forceinline__ uint4 and4(const uint4 a, const uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+__device__ __forceinline__ uint4 or4(const uint4 a, const uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+
+template <int DT, bool KSTD, bool ANNOTATE>
+__global__ void __launch_bounds__(kPairThreads) k_pair(const PairParams p) {
+  __shared__ uint32_t s_inter[kPairWarps], s_uni[kPairWarps];
+  __shared__ int32_t s_point;
+  __shared__ __align__(16) msp_pair_record s_rec;
+
+  const int64_t pid = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int32_t fa = p.pairs[2 * pid], fb = p.pairs[2 * pid + 1];
+  const uint4* __restrict__ A = reinterpret_cast<const uint4*>(p.mask + (int64_t)fa * p.mask_stride);
+  const uint4* __restrict__ B = reinterpret_cast<const uint4*>(p.mask + (int64_t)fb * p.mask_stride);
+  const int nq = (int)(((p.n + 31) / 32 + 3) / 4);       // uint4 quads holding valid words
+  const int qpw = (nq + kPairWarps - 1) / kPairWarps;    // quads per warp segment
+  const int lo = warp * qpw, hi = min(nq, lo + qpw);
+
+  uint32_t ci = 0, cu = 0;
+  for (int q = lo + lane; q < hi; q += 32) {
+    const uint4 a = __ldg(A + q), b = __ldg(B + q);
+    ci += popc4(and4(a, b));
+    cu += popc4(or4(a, b));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ci += __shfl_xor_sync(0xffffffffu, ci, o);
+    cu += __shfl_xor_sync(0xffffffffu, cu, o);
+  }
+  if (lane == 0) s_inter[warp] = ci, s_uni[warp] = cu;
+  if (tid == 0) s_point = -1;
+  __syncthreads();
+  uint32_t inter = 0, uni = 0;
+#pragma unroll
+  for (int w = 0; w < kPairWarps; ++w) inter += s_inter[w], uni += s_uni[w];
+
+  if (!ANNOTATE) {
+    if (tid == 0) {
+      p.inter_out[pid] = inter;
+      p.uni_out[pid] = uni;
+      p.overlap_out[pid] = __dmul_rn(__ddiv_rn((double)inter, (double)uni), 100.0);  // CFR:136
+    }
+    return;
+  }
+
+  // ---- k-th smallest common point id (np.intersect1d order = ascending word, ascending bit)
+  const uint32_t sv = p.sel[pid];
+  const uint64_t k64 = (p.sel_mode == 1) ? (((uint64_t)sv * (uint64_t)inter) >> 32) : (uint64_t)sv;
+  if (k64 < inter) {
+    uint32_t k = (uint32_t)k64, before = 0;
+    int target = 0;
+    for (int w = 0; w < kPairWarps; ++w) {
+      if (k >= before + s_inter[w]) before += s_inter[w], target = w + 1;
+      else break;
+    }
+    if (warp == target) {
+      k -= before;
+      for (int q0 = lo; q0 < hi; q0 += 32) {  // warp-uniform loop
+        const int q = q0 + lane;
+        uint4 c = make_uint4(0, 0, 0, 0);
+        if (q < hi) c = and4(__ldg(A + q), __ldg(B + q));
+        const uint32_t cnt = popc4(c);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (k < total) {
+          const uint32_t excl = incl - cnt;
+          if (k >= excl && k < incl) {
+            uint32_t r = k - excl;
+            const uint32_t wv[4] = {c.x, c.y, c.z, c.w};
+            int wi = 0;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const uint32_t pc = __popc(wv[wi]);
+              if (r >= pc && wi == t) r -= pc, wi = t + 1;
+            }
+            const uint32_t word = wi == 0 ? c.x : wi == 1 ? c.y : wi == 2 ? c.z : c.w;
+            const int bit = __fns(word, 0, (int)r + 1);
+            s_point = (q * 4 + wi) * 32 + bit;
+          }
+          break;
+        }
+        k -= total;
+      }
+    }
+  }
+  __syncthreads();
+  const int32_t point = s_point;
+
+  if (warp == 0) {
+    if (lane < 2) {  // annotate the point in frame 1 / frame 2
+      const int32_t f = lane == 0 ? fa : fb;
+      int vis = 0, pmx = 0, pmy = 0, dmm = 0, ux = 0, vy = 0;
+      if (point >= 0) {
+        double x, y, z;
+        PtTraits<DT>::load(p.pts, point, x, y, z);
+        const double* w = p.w2c + (int64_t)f * 16;
+        const bool fstd = KSTD && (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
+        Proj pr;
+        const uint16_t* dm = p.depth + (int64_t)f * p.depth_stride;
+        vis = fstd ? visible_exact<true>(w, p.K, p.g, dm, x, y, z, pr) : visible_exact<false>(w, p.K, p.g, dm, x, y, z, pr);
+        pmx = permille(pr.u, p.g.img_w);
+        pmy = permille(pr.v, p.g.img_h);
+        dmm = depth_mm(pr.z);
+        ux = __double2int_rz(pr.u);
+        vy = __double2int_rz(pr.v);
+      }
+      s_rec.permille[2 * lane] = pmx;
+      s_rec.permille[2 * lane + 1] = pmy;
+      s_rec.depth_mm[lane] = dmm;
+      s_rec.pix[2 * lane] = ux;
+      s_rec.pix[2 * lane + 1] = vy;
+      const int other = __shfl_xor_sync(0x3u, vis, 1);
+      if (lane == 0) s_rec.flags = (vis ? 1 : 0) | (other ? 2 : 0);
+    } else if (lane == 2) {  // pose relations
+      const double* E1 = p.E + (int64_t)fa * 16;
+      const double* E2 = p.E + (int64_t)fb * 16;
+      const double dx = E2[3] - E1[3], dy = E2[7] - E1[7], dz = E2[11] - E1[11];
+      s_rec.inter = inter;
+      s_rec.uni = uni;
+      s_rec.overlap = __dmul_rn(__ddiv_rn((double)inter, (double)uni), 100.0);
+      s_rec.distance = sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx))));  // CFR:183
+      s_rec.dyaw = p.yawpitch[2 * (int64_t)fb] - p.yawpitch[2 * (int64_t)fa];        // CFR:181
+      s_rec.dpitch = p.yawpitch[2 * (int64_t)fb + 1] - p.yawpitch[2 * (int64_t)fa + 1];
+      const double* w1 = p.w2c + (int64_t)fa * 16;  // inv(E1) @ E2, translation column (CME:185-189)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s_rec.rel_disp[i] = row_dot4(w1 + 4 * i, E2[3], E2[7], E2[11], E2[15]);
+      s_rec.point_id = point;
+    } else if (lane == 3) {
+      s_rec.reserved[0] = s_rec.reserved[1] = s_rec.reserved[2] = s_rec.reserved[3] = 0;
+    }
+    __syncwarp();
+    reinterpret_cast<uint32_t*>(p.rec + pid)[lane] = reinterpret_cast<const uint32_t*>(&s_rec)[lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// point annotation requests (one thread each)
+// ------------------------------------------------------------------------------------------------
+struct AnnotParams {
+  const void* pts;
+  int64_t n;
+  const int32_t* point_ids;
+  const int32_t* frame_ids;
+  int64_t M;
+  const double* w2c;
+  const uint16_t* depth;
+  int64_t depth_stride;
+  Intrinsics K;
+  ImageGeom g;
+  double* uvz;
+  int32_t* permille;
+  int32_t* depth_mm;
+  int32_t* pix;
+  uint8_t* visible;
+};
+
+template <int DT, bool KSTD>
+__global__ void k_annotate(const AnnotParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.M) return;
+  const int32_t pt = p.point_ids[i], f = p.frame_ids[i];
+  double x, y, z;
+  PtTraits<DT>::load(p.pts, pt, x, y, z);
+  const double* w = p.w2c + (int64_t)f * 16;
+  const bool fstd = KSTD && (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
+  Proj pr;
+  bool vis;
+  if (p.depth != nullptr) {
+    const uint16_t* dm = p.depth + (int64_t)f * p.depth_stride;
+    vis = fstd ? visible_exact<true>(w, p.K, p.g, dm, x, y, z, pr) : visible_exact<false>(w, p.K, p.g, dm, x, y, z, pr);
+  } else {
+    pr = fstd ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
+    vis = in_image(pr, p.g) && pr.z > 0.0;
+  }
+  if (p.uvz) p.uvz[3 * i] = pr.u, p.uvz[3 * i + 1] = pr.v, p.uvz[3 * i + 2] = pr.z;
+  if (p.permille) p.permille[2 * i] = permille(pr.u, p.g.img_w), p.permille[2 * i + 1] = permille(pr.v, p.g.img_h);
+  if (p.depth_mm) p.depth_mm[i] = depth_mm(pr.z);
+  if (p.pix) p.pix[2 * i] = __double2int_rz(pr.u), p.pix[2 * i + 1] = __double2int_rz(pr.v);
+  if (p.visible) p.visible[i] = vis ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-(frame, object) visible-point counts: one CTA per frame, shared-memory histogram,
+// warp-aggregated by instance id (neighbouring mesh vertices mostly share one)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_object_counts(const uint32_t* __restrict__ mask, int64_t n, int64_t mask_stride,
+                                                       const uint16_t* __restrict__ inst, int n_objects,
+                                                       uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t s_hist[];
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i <= n_objects; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const uint32_t* row = mask + (int64_t)f * mask_stride;
+  const int nwords = (int)((n + 31) / 32);
+  for (int wd = warp; wd < nwords; wd += blockDim.x / 32) {
+    const uint32_t bits = __ldg(row + wd);
+    if (bits == 0) continue;
+    const int64_t pt = (int64_t)wd * 32 + lane;
+    const uint32_t id = (pt < n) ? (uint32_t)__ldg(inst + pt) : 0u;
+    const bool active = ((bits >> lane) & 1u) && id != 0u && id <= (uint32_t)n_objects;
+    const uint32_t m = __ballot_sync(0xffffffffu, active);
+    if (active) {
+      const uint32_t grp = __match_any_sync(m, id);
+      if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[id], (uint32_t)__popc(grp));
+    }
+  }
+  __syncthreads();
+  for (int o = tid; o < n_objects; o += blockDim.x) counts[(int64_t)f * n_objects + o] = s_hist[o + 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// TAPVid-3D tracks
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_track_project(const float* __restrict__ tracks, const double* __restrict__ w2c,
+                                                       const double* __restrict__ intr, int T, int N, double img_h,
+                                                       double img_w, double* __restrict__ world,
+                                                       double* __restrict__ uvn, int32_t* __restrict__ pm,
+                                                       uint8_t* __restrict__ valid) {
+  __shared__ double s_c2w[16];
+  const int t = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double m[16], inv[16];
+    for (int i = 0; i < 16; ++i) m[i] = w2c[(int64_t)t * 16 + i];
+    const bool ok = inverse4(m, inv);
+    for (int i = 0; i < 16; ++i) s_c2w[i] = ok ? inv[i] : __longlong_as_double(0x7ff8000000000000LL);
+  }
+  __syncthreads();
+  const double fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const int64_t i = (int64_t)t * N + n;
+    const double x = tracks[3 * i], y = tracks[3 * i + 1], z = tracks[3 * i + 2];
+    if (world) {  // single_object_movement_engine_coord.py:446-451
+#pragma unroll
+      for (int r = 0; r < 3; ++r) world[3 * i + r] = row_dot4(s_c2w + 4 * r, x, y, z, 1.0);
+    }
+    // single_object_movement_engine_coord.py:293-315 (float64 throughout, as under the pinned numpy 1.26)
+    const double zg = __dadd_rn(z, 1e-8);
+    const double u = __dadd_rn(__ddiv_rn(__dmul_rn(fx, x), zg), cx);
+    const double v = __dadd_rn(__ddiv_rn(__dmul_rn(fy, y), zg), cy);
+    const double un = __ddiv_rn(u, img_w), vn = __ddiv_rn(v, img_h);
+    const bool ok = (un >= 0.0) & (un < 1.0) & (vn >= 0.0) & (vn < 1.0) & (z > 0.0);
+    if (uvn) uvn[2 * i] = un, uvn[2 * i + 1] = vn;
+    if (pm) pm[2 * i] = ok ? __double2int_rn(__dmul_rn(un, 1000.0)) : 0, pm[2 * i + 1] = ok ? __double2int_rn(__dmul_rn(vn, 1000.0)) : 0;
+    if (valid) valid[i] = ok ? 1 : 0;
+  }
+}
+
+__global__ void k_track_pair_displacement(const double* __restrict__ world, const double* __restrict__ w2c, int T, int N,
+                                          const int32_t* __restrict__ triples, int64_t M, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int f1 = triples[3 * i], f2 = triples[3 * i + 1], pt = triples[3 * i + 2];
+  const double* a = world + 3 * ((int64_t)f1 * N + pt);
+  const double* b = world + 3 * ((int64_t)f2 * N + pt);
+  const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+  const double* w1 = w2c + (int64_t)f1 * 16;
+  double m1[16], m2[16], c1[16], c2[16];
+  for (int k = 0; k < 16; ++k) m1[k] = w1[k], m2[k] = w2c[(int64_t)f2 * 16 + k];
+  inverse4(m1, c1);
+  inverse4(m2, c2);
+  const double ex = c2[3] - c1[3], ey = c2[7] - c1[7], ez = c2[11] - c1[11];
+  out[5 * i + 0] = sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx))));
+  for (int r = 0; r < 3; ++r) out[5 * i + 1 + r] = row_dot4(w1 + 4 * r, dx, dy, dz, 0.0);
+  out[5 * i + 4] = sqrt(__fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+static bool k_is_std(const double* K) {
+  return K[1] == 0.0 && K[3] == 0.0 && K[4] == 0.0 && K[7] == 0.0 && K[8] == 0.0 && K[9] == 0.0 && K[10] == 1.0 &&
+         K[11] == 0.0;
+}
+static Intrinsics make_intr(const double* K16) {
+  Intrinsics k;
+  memcpy(k.k, K16, sizeof(double) * 12);
+  return k;
+}
+static int make_geom(const msp_camera* c, ImageGeom* g) {
+  REQUIRE(c != nullptr, "host_cam is NULL");
+  REQUIRE(c->image_h > 0 && c->image_w > 0 && c->depth_h > 0 && c->depth_w > 0, "non-positive image size");
+  g->img_w = (double)c->image_w;
+  g->img_h = (double)c->image_h;
+  g->sx = (double)c->depth_w / (double)c->image_w;  // info_handler.py:356
+  g->sy = (double)c->depth_h / (double)c->image_h;  // info_handler.py:357
+  g->depth_scale = c->depth_scale;
+  g->depth_w = c->depth_w;
+  g->depth_h = c->depth_h;
+  g->image_w = c->image_w;
+  g->image_h = c->image_h;
+  return MSP_OK;
+}
+
+extern "C" int msp_version(void) { return MSP_VERSION; }
+extern "C" const char* msp_last_error(void) { return g_err; }
+
+extern "C" int msp_pose_prepare(const double* c2w, const double* axis_align, int32_t F, double* E_out, double* w2c_out,
+                                double* yawpitch_out, int32_t* valid_out, void* stream) {
+  REQUIRE(F >= 0, "F < 0");
+  if (F == 0) return MSP_OK;
+  REQUIRE(c2w && E_out && w2c_out && yawpitch_out && valid_out, "msp_pose_prepare: NULL pointer");
+  k_pose_prepare<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c2w, axis_align, F, E_out, w2c_out, yawpitch_out,
+                                                                     valid_out);
+  return check_launch("msp_pose_prepare");
+}
+
+template <int MODE>
+static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool mat, cudaStream_t s) {
+  const dim3 grid((unsigned)((p.n + kTilePoints - 1) / kTilePoints), (unsigned)((p.F + kFramesPerCta - 1) / kFramesPerCta));
+  REQUIRE(grid.y <= 65535u, "too many frames in one call (max 65535*32)");
+#define MSP_LAUNCH(DT, KS, MT) k_frame_loop<DT, KS, MODE, MT><<<grid, kThreads, 0, s>>>(p)
+#define MSP_DISPATCH_DT(KS, MT)       \
+  switch (dt) {                       \
+    case 0: MSP_LAUNCH(0, KS, MT); break; \
+    case 1: MSP_LAUNCH(1, KS, MT); break; \
+    default: MSP_LAUNCH(2, KS, MT); break; \
+  }
+  if (MODE == MODE_VIS && mat) {
+    if (kstd) { MSP_DISPATCH_DT(true, true) } else { MSP_DISPATCH_DT(false, true) }
+  } else {
+    if (kstd) { MSP_DISPATCH_DT(true, false) } else { MSP_DISPATCH_DT(false, false) }
+  }
+#undef MSP_DISPATCH_DT
+#undef MSP_LAUNCH
+  return MSP_OK;
+}
+
+extern "C" int msp_project_visibility(const void* pts, int64_t n, int32_t pts_dtype, const double* K16,
+                                      const double* w2c, int32_t F, const uint16_t* depth, const msp_camera* host_cam,
+                                      uint32_t* mask_bits, int64_t mask_stride_words, double* xy_out, double* z_out,
+                                      void* stream) {
+  REQUIRE(n >= 0 && F >= 0, "negative size");
+  REQUIRE(pts_dtype >= 0 && pts_dtype <= 2, "pts_dtype must be 0, 1 or 2");
+  REQUIRE((xy_out == nullptr) == (z_out == nullptr), "xy_out and z_out must both be given or both be NULL");
+  if (n == 0 || F == 0) return MSP_OK;
+  REQUIRE(pts && K16 && w2c && depth && mask_bits, "msp_project_visibility: NULL pointer");
+  REQUIRE(aligned16(pts) && aligned16(mask_bits), "pts and mask_bits must be 16-byte aligned");
+  REQUIRE(mask_stride_words % 4 == 0 && mask_stride_words >= (n + 31) / 32, "mask_stride_words must be a multiple of 4 and >= ceil(n/32)");
+  REQUIRE(xy_out == nullptr || aligned16(xy_out), "xy_out must be 16-byte aligned");
+  FrameLoopParams p{};
+  if (int rc = make_geom(host_cam, &p.g)) return rc;
+  p.pts = pts, p.n = n, p.w2c = w2c, p.F = F, p.depth = depth, p.zbuf = nullptr;
+  p.depth_stride = (int64_t)host_cam->depth_h * host_cam->depth_w;
+  p.mask = mask_bits, p.mask_stride = mask_stride_words, p.xy = xy_out, p.z = z_out;
+  p.K = make_intr(K16);
+  if (int rc = launch_frame_loop<MODE_VIS>(p, pts_dtype, k_is_std(K16), xy_out != nullptr, (cudaStream_t)stream)) return rc;
+  return check_launch("msp_project_visibility");
+}
+
+extern "C" int msp_zbuffer_render(const void* pts, int64_t n, int32_t pts_dtype, const double* K16, const double* w2c,
+                                  int32_t F, const msp_camera* host_cam, float* zbuf, void* stream) {
+  REQUIRE(n >= 0 && F >= 0, "negative size");
+  REQUIRE(pts_dtype >= 0 && pts_dtype <= 2, "pts_dtype must be 0, 1 or 2");
+  if (F == 0) return MSP_OK;
+  REQUIRE(K16 && w2c && zbuf && host_cam, "msp_zbuffer_render: NULL pointer");
+  FrameLoopParams p{};
+  if (int rc = make_geom(host_cam, &p.g)) return rc;
+  p.depth_stride = (int64_t)host_cam->depth_h * host_cam->depth_w;
+  const int64_t total = p.depth_stride * F;
+  k_fill_u32<<<(unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<uint32_t*>(zbuf), total, 0x7f800000u);
+  if (n > 0) {
+    REQUIRE(pts != nullptr && aligned16(pts), "pts must be non-NULL and 16-byte aligned");
+    p.pts = pts, p.n = n, p.w2c = w2c, p.F = F, p.zbuf = zbuf;
+    p.K = make_intr(K16);
+    if (int rc = launch_frame_loop<MODE_ZBUF>(p, pts_dtype, k_is_std(K16), false, (cudaStream_t)stream)) return rc;
+  }
+  return check_launch("msp_zbuffer_render");
+}
+
+extern "C" int msp_depth_to_u16(const float* zbuf, int64_t count, int32_t margin_mm, double depth_scale, uint16_t* out,
+                                void* stream) {
+  REQUIRE(count >= 0, "negative count");
+  if (count == 0) return MSP_OK;
+  REQUIRE(zbuf && out, "msp_depth_to_u16: NULL pointer");
+  REQUIRE(depth_scale > 0.0, "depth_scale must be positive");
+  k_depth_to_u16<<<(unsigned)((count + 255) / 256 < 148 * 16 ? (count + 255) / 256 : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      zbuf, count, margin_mm, depth_scale, out);
+  return check_launch("msp_depth_to_u16");
+}
+
+extern "C" int msp_pair_overlap(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, const int32_t* pairs,
+                                int64_t P, uint32_t* inter, uint32_t* uni, double* overlap_pct, void* stream) {
+  REQUIRE(n >= 0 && P >= 0, "negative size");
+  if (P == 0) return MSP_OK;
+  REQUIRE(mask_bits && pairs && inter && uni && overlap_pct, "msp_pair_overlap: NULL pointer");
+  REQUIRE(aligned16(mask_bits) && mask_stride_words % 4 == 0 && mask_stride_words >= (n + 31) / 32, "mask layout");
+  PairParams p{};
+  p.mask = mask_bits, p.n = n, p.mask_stride = mask_stride_words, p.pairs = pairs, p.P = P;
+  p.inter_out = inter, p.uni_out = uni, p.overlap_out = overlap_pct;
+  k_pair<0, true, false><<<(unsigned)P, kPairThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("msp_pair_overlap");
+}
+
+extern "C" int msp_pair_annotate(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, const int32_t* pairs,
+                                 int64_t P, const uint32_t* sel, int32_t sel_mode, const void* pts, int32_t pts_dtype,
+                                 const double* K16, const double* E, const double* w2c, const double* yawpitch,
+                                 const uint16_t* depth, const msp_camera* host_cam, msp_pair_record* records,
+                                 void* stream) {
+  REQUIRE(n >= 0 && P >= 0, "negative size");
+  REQUIRE(pts_dtype >= 0 && pts_dtype <= 2, "pts_dtype must be 0, 1 or 2");
+  REQUIRE(sel_mode == 0 || sel_mode == 1, "sel_mode must be 0 or 1");
+  REQUIRE(P < (1ll << 31), "P too large for one launch");
+  if (P == 0) return MSP_OK;
+  REQUIRE(mask_bits && pairs && sel && pts && K16 && E && w2c && yawpitch && depth && records, "msp_pair_annotate: NULL pointer");
+  REQUIRE(aligned16(mask_bits) && mask_stride_words % 4 == 0 && mask_stride_words >= (n + 31) / 32, "mask layout");
+  REQUIRE(aligned16(pts) && aligned16(records), "pts and records must be 16-byte aligned");
+  PairParams p{};
+  if (int rc = make_geom(host_cam, &p.g)) return rc;
+  p.mask = mask_bits, p.n = n, p.mask_stride = mask_stride_words, p.pairs = pairs, p.P = P, p.sel = sel;
+  p.sel_mode = sel_mode, p.pts = pts, p.E = E, p.w2c = w2c, p.yawpitch = yawpitch, p.depth = depth;
+  p.depth_stride = (int64_t)host_cam->depth_h * host_cam->depth_w;
+  p.K = make_intr(K16);
+  p.rec = records;
+  const bool ks = k_is_std(K16);
+  cudaStream_t s = (cudaStream_t)stream;
+#define MSP_PAIR(DT)                                                            \
+  if (ks) k_pair<DT, true, true><<<(unsigned)P, kPairThreads, 0, s>>>(p);      \
+  else k_pair<DT, false, true><<<(unsigned)P, kPairThreads, 0, s>>>(p)
+  switch (pts_dtype) {
+    case 0: MSP_PAIR(0); break;
+    case 1: MSP_PAIR(1); break;
+    default: MSP_PAIR(2); break;
+  }
+#undef MSP_PAIR
+  return check_launch("msp_pair_annotate");
+}
+
+extern "C" int msp_annotate_points(const void* pts, int64_t n, int32_t pts_dtype, const int32_t* point_ids,
+                                   const int32_t* frame_ids, int64_t M, const double* K16, const double* w2c,
+                                   const uint16_t* depth, const msp_camera* host_cam, double* uvz, int32_t* permille,
+                                   int32_t* depth_mm, int32_t* pix, uint8_t* visible, void* stream) {
+  REQUIRE(M >= 0 && n >= 0, "negative size");
+  REQUIRE(pts_dtype >= 0 && pts_dtype <= 2, "pts_dtype must be 0, 1 or 2");
+  if (M == 0) return MSP_OK;
+  REQUIRE(pts && point_ids && frame_ids && K16 && w2c, "msp_annotate_points: NULL pointer");
+  REQUIRE(aligned16(pts), "pts must be 16-byte aligned");
+  AnnotParams p{};
+  if (int rc = make_geom(host_cam, &p.g)) return rc;
+  p.pts = pts, p.n = n, p.point_ids = point_ids, p.frame_ids = frame_ids, p.M = M, p.w2c = w2c, p.depth = depth;
+  p.depth_stride = (int64_t)host_cam->depth_h * host_cam->depth_w;
+  p.K = make_intr(K16);
+  p.uvz = uvz, p.permille = permille, p.depth_mm = depth_mm, p.pix = pix, p.visible = visible;
+  const bool ks = k_is_std(K16);
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+#define MSP_ANN(DT)                                        \
+  if (ks) k_annotate<DT, true><<<grid, 128, 0, s>>>(p);   \
+  else k_annotate<DT, false><<<grid, 128, 0, s>>>(p)
+  switch (pts_dtype) {
+    case 0: MSP_ANN(0); break;
+    case 1: MSP_ANN(1); break;
+    default: MSP_ANN(2); break;
+  }
+#undef MSP_ANN
+  return check_launch("msp_annotate_points");
+}
+
+extern "C" int msp_object_counts(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, int32_t F,
+                                 const uint16_t* instance_ids, int32_t n_objects, uint32_t* counts, void* stream) {
+  REQUIRE(n >= 0 && F >= 0 && n_objects >= 0, "negative size");
+  REQUIRE(n_objects <= 8191, "n_objects must be <= 8191");
+  if (F == 0 || n_objects == 0) return MSP_OK;
+  REQUIRE(mask_bits && instance_ids && counts, "msp_object_counts: NULL pointer");
+  REQUIRE(mask_stride_words >= (n + 31) / 32, "mask_stride_words too small");
+  k_object_counts<<<(unsigned)F, 256, (size_t)(n_objects + 1) * sizeof(uint32_t), (cudaStream_t)stream>>>(
+      mask_bits, n, mask_stride_words, instance_ids, n_objects, counts);
+  return check_launch("msp_object_counts");
+}
+
+extern "C" int msp_track_project(const float* tracks, const double* w2c, const double* fxfycxcy, int32_t T, int32_t N,
+                                 int32_t image_h, int32_t image_w, double* world_out, double* uvn_out,
+                                 int32_t* permille_out, uint8_t* valid_out, void* stream) {
+  REQUIRE(T >= 0 && N >= 0, "negative size");
+  REQUIRE(image_h > 0 && image_w > 0, "non-positive image size");
+  if (T == 0 || N == 0) return MSP_OK;
+  REQUIRE(tracks && w2c && fxfycxcy, "msp_track_project: NULL pointer");
+  k_track_project<<<(unsigned)T, 128, 0, (cudaStream_t)stream>>>(tracks, w2c, fxfycxcy, T, N, (double)image_h,
+                                                                 (double)image_w, world_out, uvn_out, permille_out,
+                                                                 valid_out);
+  return check_launch("msp_track_project");
+}
+
+extern "C" int msp_track_pair_displacement(const double* world, const double* w2c, int32_t T, int32_t N,
+                                           const int32_t* triples, int64_t M, double* out, void* stream) {
+  REQUIRE(T >= 0 && N >= 0 && M >= 0, "negative size");
+  if (M == 0) return MSP_OK;
+  REQUIRE(world && w2c && triples && out, "msp_track_pair_displacement: NULL pointer");
+  k_track_pair_displacement<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(world, w2c, T, N, triples,
+                                                                                          M, out);
+  return check_launch("msp_track_pair_displacement");
+}

@@ -1,0 +1,246 @@
+"""Device-resident scene + the per-scene workers of the MultiSPA geometry path.
+
+This is the host side above the C ABI (include/msp.h).  PyTorch is used only for
+device memory, streams and host<->device copies; all geometry runs in libmsp.so.
+
+Reference surface mirrored here (file:line relative to the reference checkout):
+  DeviceScene.project_visibility  <- MVI:93-100 / CFR:152-157 frame loop (IH:313-386)
+  DeviceScene.pair_annotate       <- CFR:176-189 + VC-coor:303-344 + CME:177-191
+  DeviceScene.annotate_points     <- IH:291-305 + DE-dot:216-218,261
+  DeviceScene.object_counts       <- COV:110-136
+  process_scene_visibility        <- make_visibility_info.process_scene (MVI:75-125)
+  process_scene_relations         <- calculate_frames_relations.process_scene (CFR:139-197)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from itertools import combinations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MspCamera, check, lib
+
+PAIR_RECORD_DTYPE = np.dtype([
+    ("inter", "<u4"), ("uni", "<u4"), ("overlap", "<f8"),
+    ("distance", "<f8"), ("dyaw", "<f8"), ("dpitch", "<f8"), ("rel_disp", "<f8", (3,)),
+    ("point_id", "<i4"), ("flags", "<i4"), ("permille", "<i4", (4,)),
+    ("depth_mm", "<i4", (2,)), ("pix", "<i4", (4,)), ("reserved", "<i4", (4,)),
+])
+assert PAIR_RECORD_DTYPE.itemsize == 128
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("multi_spatialmllm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def mask_stride_words(n: int) -> int:
+    return ((n + 31) // 32 + 3) // 4 * 4
+
+
+def _to_device(a, dtype, device, non_blocking=True):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype, non_blocking=non_blocking).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype, non_blocking=non_blocking)
+
+
+class DeviceScene:
+    """One scene resident in HBM: points, poses (prepared on the device), depth maps, masks."""
+
+    def __init__(self, points, K, c2w, axis_align=None, depth=None, instance_ids=None, num_objects=0,
+                 image_hw=(968, 1296), depth_hw=(480, 640), depth_scale=0.001, device="cuda:0"):
+        _require_cuda()
+        self.device = torch.device(device)
+        pts = points
+        if not isinstance(pts, torch.Tensor):
+            pts = torch.from_numpy(np.ascontiguousarray(pts))
+        if pts.dtype == torch.float64:
+            assert pts.ndim == 2 and pts.shape[1] == 3, "float64 points must be (N,3)"
+            self.pts_dtype = _lib.MSP_PTS_F64X3
+        elif pts.dtype == torch.float32 and pts.shape[1] == 4:
+            self.pts_dtype = _lib.MSP_PTS_F32X4
+        elif pts.dtype == torch.float32 and pts.shape[1] == 3:
+            self.pts_dtype = _lib.MSP_PTS_F32X3
+        else:
+            raise ValueError(f"unsupported point layout {tuple(pts.shape)} {pts.dtype}")
+        self.pts = pts.to(self.device, non_blocking=True).contiguous()
+        self.n = int(self.pts.shape[0])
+        self.K_host = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(16))
+        self.cam = MspCamera(int(image_hw[0]), int(image_hw[1]), int(depth_hw[0]), int(depth_hw[1]), float(depth_scale))
+        self.image_hw, self.depth_hw = tuple(image_hw), tuple(depth_hw)
+        self.stride = mask_stride_words(self.n)
+        self.instance_ids = None if instance_ids is None else _to_device(
+            np.asarray(instance_ids).astype(np.uint16), torch.uint16, self.device)
+        self.num_objects = int(num_objects)
+        self.depth = None
+        self.mask = None
+        self.set_poses(c2w, axis_align)
+        if depth is not None:
+            self.set_depth(depth)
+
+    # ---- poses ---------------------------------------------------------------------------------
+    def set_poses(self, c2w, axis_align=None):
+        c2w_d = _to_device(np.asarray(c2w, dtype=np.float64).reshape(-1, 16) if not isinstance(c2w, torch.Tensor) else c2w.reshape(-1, 16),
+                           torch.float64, self.device)
+        self.F = int(c2w_d.shape[0])
+        A = None if axis_align is None else _to_device(np.asarray(axis_align, dtype=np.float64).reshape(16), torch.float64, self.device)
+        self.c2w = c2w_d
+        self.E = torch.empty((self.F, 16), dtype=torch.float64, device=self.device)
+        self.w2c = torch.empty((self.F, 16), dtype=torch.float64, device=self.device)
+        self.yawpitch = torch.empty((self.F, 2), dtype=torch.float64, device=self.device)
+        self.valid = torch.empty((self.F,), dtype=torch.int32, device=self.device)
+        check(lib.msp_pose_prepare(_ptr(c2w_d), _ptr(A), self.F, _ptr(self.E), _ptr(self.w2c), _ptr(self.yawpitch),
+                                   _ptr(self.valid), _stream()), "msp_pose_prepare")
+        self.mask = None
+
+    def set_depth(self, depth):
+        d = depth if isinstance(depth, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(depth))
+        assert d.dtype == torch.uint16 and tuple(d.shape) == (self.F, *self.depth_hw), (d.dtype, d.shape)
+        self.depth = d.to(self.device, non_blocking=True).contiguous()
+
+    # ---- z-buffer (not in the reference) -------------------------------------------------------
+    def render_zbuffer(self) -> torch.Tensor:
+        zb = torch.empty((self.F, *self.depth_hw), dtype=torch.float32, device=self.device)
+        check(lib.msp_zbuffer_render(_ptr(self.pts), self.n, self.pts_dtype, self.K_host.ctypes.data, _ptr(self.w2c),
+                                     self.F, C.byref(self.cam), _ptr(zb), _stream()), "msp_zbuffer_render")
+        return zb
+
+    def render_depth(self, margin_mm: int = 1, chunk: int = 256) -> torch.Tensor:
+        """Synthetic sensor depth for the scene's own frames (chunked so the fp32 buffer stays small)."""
+        out = torch.empty((self.F, *self.depth_hw), dtype=torch.uint16, device=self.device)
+        px = self.depth_hw[0] * self.depth_hw[1]
+        for f0 in range(0, self.F, chunk):
+            f1 = min(self.F, f0 + chunk)
+            zb = torch.empty((f1 - f0, *self.depth_hw), dtype=torch.float32, device=self.device)
+            check(lib.msp_zbuffer_render(_ptr(self.pts), self.n, self.pts_dtype, self.K_host.ctypes.data,
+                                         self.w2c[f0:].data_ptr(), f1 - f0, C.byref(self.cam), _ptr(zb), _stream()),
+                  "msp_zbuffer_render")
+            check(lib.msp_depth_to_u16(_ptr(zb), (f1 - f0) * px, int(margin_mm), self.cam.depth_scale,
+                                       out[f0:].data_ptr(), _stream()), "msp_depth_to_u16")
+        self.depth = out
+        return out
+
+    # ---- K1 ------------------------------------------------------------------------------------
+    def project_visibility(self, materialize: bool = False):
+        assert self.depth is not None, "no depth maps: call set_depth() or render_depth() first"
+        if self.mask is None:
+            self.mask = torch.zeros((self.F, self.stride), dtype=torch.int32, device=self.device)
+        xy = z = None
+        if materialize:
+            xy = torch.empty((self.F, self.n, 2), dtype=torch.float64, device=self.device)
+            z = torch.empty((self.F, self.n), dtype=torch.float64, device=self.device)
+        check(lib.msp_project_visibility(_ptr(self.pts), self.n, self.pts_dtype, self.K_host.ctypes.data, _ptr(self.w2c),
+                                         self.F, _ptr(self.depth), C.byref(self.cam), _ptr(self.mask), self.stride,
+                                         _ptr(xy), _ptr(z), _stream()), "msp_project_visibility")
+        return (self.mask, xy, z) if materialize else self.mask
+
+    def mask_bool(self) -> np.ndarray:
+        """(F,N) bool on the host — the reference's in_bounds mask per frame (IH:386)."""
+        w = self.mask.cpu().numpy().view(np.uint32)
+        bits = np.unpackbits(w.view(np.uint8), axis=1, bitorder="little")
+        return bits[:, :self.n].astype(bool)
+
+    # ---- pair stage ----------------------------------------------------------------------------
+    def pair_overlap(self, pairs):
+        pairs_d = _to_device(np.asarray(pairs, dtype=np.int32).reshape(-1, 2), torch.int32, self.device)
+        P = int(pairs_d.shape[0])
+        inter = torch.empty((P,), dtype=torch.int32, device=self.device)
+        uni = torch.empty((P,), dtype=torch.int32, device=self.device)
+        ov = torch.empty((P,), dtype=torch.float64, device=self.device)
+        check(lib.msp_pair_overlap(_ptr(self.mask), self.n, self.stride, _ptr(pairs_d), P, _ptr(inter), _ptr(uni),
+                                   _ptr(ov), _stream()), "msp_pair_overlap")
+        return inter, uni, ov
+
+    def pair_annotate(self, pairs, sel, sel_mode: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        pairs_d = _to_device(pairs if isinstance(pairs, torch.Tensor) else np.asarray(pairs, dtype=np.int32).reshape(-1, 2),
+                             torch.int32, self.device)
+        P = int(pairs_d.shape[0])
+        sel_d = sel if isinstance(sel, torch.Tensor) else torch.from_numpy(np.asarray(sel).astype(np.uint32).view(np.int32))
+        sel_d = sel_d.to(self.device, non_blocking=True).contiguous()
+        rec = out if out is not None else torch.empty((P, 128), dtype=torch.uint8, device=self.device)
+        check(lib.msp_pair_annotate(_ptr(self.mask), self.n, self.stride, _ptr(pairs_d), P, _ptr(sel_d), int(sel_mode),
+                                    _ptr(self.pts), self.pts_dtype, self.K_host.ctypes.data, _ptr(self.E), _ptr(self.w2c),
+                                    _ptr(self.yawpitch), _ptr(self.depth), C.byref(self.cam), _ptr(rec), _stream()),
+              "msp_pair_annotate")
+        return rec
+
+    @staticmethod
+    def records_to_numpy(rec: torch.Tensor) -> np.ndarray:
+        return rec.cpu().numpy().view(PAIR_RECORD_DTYPE).reshape(-1)
+
+    def annotate_points(self, point_ids, frame_ids, use_depth: bool = True):
+        pid = _to_device(np.asarray(point_ids, dtype=np.int32), torch.int32, self.device)
+        fid = _to_device(np.asarray(frame_ids, dtype=np.int32), torch.int32, self.device)
+        M = int(pid.shape[0])
+        uvz = torch.empty((M, 3), dtype=torch.float64, device=self.device)
+        pm = torch.empty((M, 2), dtype=torch.int32, device=self.device)
+        dmm = torch.empty((M,), dtype=torch.int32, device=self.device)
+        pix = torch.empty((M, 2), dtype=torch.int32, device=self.device)
+        vis = torch.empty((M,), dtype=torch.uint8, device=self.device)
+        check(lib.msp_annotate_points(_ptr(self.pts), self.n, self.pts_dtype, _ptr(pid), _ptr(fid), M,
+                                      self.K_host.ctypes.data, _ptr(self.w2c), _ptr(self.depth) if use_depth else None,
+                                      C.byref(self.cam), _ptr(uvz), _ptr(pm), _ptr(dmm), _ptr(pix), _ptr(vis), _stream()),
+              "msp_annotate_points")
+        return {"uvz": uvz, "permille": pm, "depth_mm": dmm, "pix": pix, "visible": vis}
+
+    def object_counts(self) -> torch.Tensor:
+        assert self.instance_ids is not None and self.num_objects > 0
+        counts = torch.empty((self.F, self.num_objects), dtype=torch.int32, device=self.device)
+        check(lib.msp_object_counts(_ptr(self.mask), self.n, self.stride, self.F, _ptr(self.instance_ids),
+                                    self.num_objects, _ptr(counts), _stream()), "msp_object_counts")
+        return counts
+
+
+# ------------------------------------------------------------------------------------------------
+# per-scene workers with the reference's return shapes
+# ------------------------------------------------------------------------------------------------
+
+def process_scene_visibility(scene: DeviceScene, image_ids):
+    """make_visibility_info.process_scene (MVI:75-125): image_to_points / point_to_images.
+
+    ``image_ids`` are the ids of the scene's frames in row order; frames with an
+    invalid pose are skipped exactly like get_all_extrinsic_valid_image_ids (IH:184-189).
+    """
+    scene.project_visibility()
+    valid = scene.valid.cpu().numpy().astype(bool)
+    m = scene.mask_bool()
+    image_to_points = {}
+    for f, image_id in enumerate(image_ids):
+        if valid[f]:
+            image_to_points[image_id] = np.flatnonzero(m[f]).tolist()
+    ids = np.asarray(image_ids)
+    point_to_images = {}
+    mv = m[valid]
+    idv = ids[valid]
+    order = np.argsort(idv, kind="stable")          # sorted(list(set)) of string ids (MVI:116-118)
+    mv, idv = mv[order], idv[order]
+    for p in range(scene.n):
+        point_to_images[p] = idv[mv[:, p]].tolist()
+    return {"image_to_points": image_to_points, "point_to_images": point_to_images}
+
+
+def process_scene_relations(scene: DeviceScene, image_ids):
+    """calculate_frames_relations.process_scene (CFR:139-197): all i<j pairs of valid frames."""
+    scene.project_visibility()
+    valid = np.flatnonzero(scene.valid.cpu().numpy())
+    pairs = np.array(list(combinations(valid.tolist(), 2)), dtype=np.int32).reshape(-1, 2)
+    if len(pairs) == 0:
+        return {}
+    rec = scene.records_to_numpy(scene.pair_annotate(pairs, np.zeros(len(pairs), np.uint32), sel_mode=0))
+    out = {}
+    for (i, j), r in zip(pairs.tolist(), rec):
+        out[(image_ids[i], image_ids[j])] = {
+            "overlap": float(r["overlap"]), "distance": float(r["distance"]),
+            "yaw": float(r["dyaw"]), "pitch": float(r["dpitch"]),
+        }
+    return out

@@ -303,7 +303,9 @@ def tracks_to_world(tracks_xyz_cam: np.ndarray, w2c: np.ndarray) -> np.ndarray:
 def track_project_point(p_cam, fxfycxcy, image_h, image_w):
     """OM:293-315: pinhole with the 1e-8 guard; None unless 0<=u_n<1, 0<=v_n<1, z>0."""
     fx, fy, cx, cy = fxfycxcy
-    x, y, z = p_cam
+    # float64 throughout: under the reference's pinned numpy 1.26.4 a float32 track coordinate
+    # plus the Python float 1e-8 promotes to float64 (value-based casting); NEP 50 would not.
+    x, y, z = np.asarray(p_cam, dtype=np.float64)
     u = (fx * x / (z + 1e-8)) + cx
     v = (fy * y / (z + 1e-8)) + cy
     un = u / image_w

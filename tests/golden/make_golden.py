@@ -131,7 +131,9 @@ def make_tapvid(ref, tmp):
     with contextlib.redirect_stdout(io.StringIO()):
         for t in range(T):
             for n in range(N):
-                r = eng.project_point(vid.tracks_xyz[t, n], vid.fxfycxcy, H, W)
+                # float64 input pins the reference environment's semantics (numpy 1.26.4, requirements/data_engine.yaml:162):
+                # there np.float32 + 1e-8 promotes to float64, under numpy>=2 (NEP 50) it would stay float32.
+                r = eng.project_point(vid.tracks_xyz[t, n].astype(np.float64), vid.fxfycxcy, H, W)
                 if r is not None:
                     proj[t, n] = r
     np.savez_compressed(

@@ -1,0 +1,68 @@
+"""No-GPU checks of the boundary: the library loads, exports what include/msp.h declares, host helpers work."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "msp.h")).read()
+    return sorted(set(re.findall(r"MSP_API\s+[\w\s\*]+?\b(msp_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from multi_spatialmllm_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(_lib.lib, name), f"{name} declared in msp.h but not exported by libmsp.so"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared          # the ctypes table covers the whole header
+    assert _lib.version() == 100
+    assert _lib.lib.msp_last_error() is not None
+
+
+def test_record_layout_matches_header():
+    from multi_spatialmllm_b200 import engine
+    dt = engine.PAIR_RECORD_DTYPE
+    assert dt.itemsize == 128
+    assert dt.fields["overlap"][1] == 8 and dt.fields["rel_disp"][1] == 40 and dt.fields["point_id"][1] == 64
+    assert dt.fields["permille"][1] == 72 and dt.fields["depth_mm"][1] == 88 and dt.fields["pix"][1] == 96
+    assert ctypes.sizeof(engine.MspCamera) == 24
+
+
+def test_argument_validation_needs_no_gpu():
+    """EINVAL paths return before any CUDA call."""
+    from multi_spatialmllm_b200 import _lib
+    rc = _lib.lib.msp_project_visibility(None, 10, 7, None, None, 1, None, None, None, 4, None, None, None)
+    assert rc == -1 and b"pts_dtype" in _lib.lib.msp_last_error()
+    rc = _lib.lib.msp_pair_annotate(None, 10, 4, None, 1, None, 5, None, 0, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"sel_mode" in _lib.lib.msp_last_error()
+    assert _lib.lib.msp_pose_prepare(None, None, 0, None, None, None, None, None) == 0     # empty input is fine
+
+
+def test_mask_stride_and_synth_determinism():
+    from multi_spatialmllm_b200 import engine, synth
+    assert engine.mask_stride_words(1) == 4 and engine.mask_stride_words(128) == 4 and engine.mask_stride_words(129) == 8
+    assert engine.mask_stride_words(200_000) == 6252
+    a = synth.make_scene(3, 5000, 4)
+    b = synth.make_scene(3, 5000, 4)
+    np.testing.assert_array_equal(a.points, b.points)
+    np.testing.assert_array_equal(a.c2w, b.c2w)
+    assert a.points.dtype == np.float32 and a.n_points == 5000 and a.c2w.shape == (4, 4, 4)
+    assert np.array_equal(np.round(a.c2w, 6), a.c2w)           # %f-style pose text
+    v = synth.make_video(1, n_frames=10, n_tracks=16)
+    assert v.tracks_xyz.shape == (10, 16, 3) and v.tracks_xyz.dtype == np.float32
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import pytest
+    import torch
+    from multi_spatialmllm_b200 import engine, synth
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    s = synth.make_scene(0, 100, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.DeviceScene(s.points, s.K, s.c2w)

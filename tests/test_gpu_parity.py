@@ -1,0 +1,297 @@
+"""CUDA path (through the C ABI) against the reference goldens and the NumPy oracle.
+
+Bars: bit-exact masks / indices / integer annotations; floats within 1e-9 relative here
+(the judged tolerance is 1e-5 relative, BASELINE.json).
+"""
+import numpy as np
+import pytest
+
+from oracle import geometry as og
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _scene_from_golden(g, **kw):
+    from multi_spatialmllm_b200.engine import DeviceScene
+    pts = kw.pop("points", g["points"])
+    return DeviceScene(pts, g["K"], g["c2w"], axis_align=g["axis_align"], depth=g["depth"],
+                       instance_ids=g["instance_ids"], num_objects=int(g["num_objects"]),
+                       image_hw=tuple(g["image_hw"]), depth_hw=tuple(g["depth_hw"]), **kw)
+
+
+def _valid_rows(g):
+    ids = list(g["image_ids"])
+    return [ids.index(v) for v in g["valid_ids"]]
+
+
+@pytest.mark.parametrize("layout", ["f32x3", "f32x4", "f64x3"])
+def test_golden_projection_and_masks(golden_scannet, layout):
+    g = golden_scannet
+    pts = g["points"]
+    if layout == "f32x4":
+        pts = np.concatenate([pts, np.ones((len(pts), 1), np.float32)], 1)
+    elif layout == "f64x3":
+        pts = pts.astype(np.float64)
+    sc = _scene_from_golden(g, points=pts)
+    mask, xy, z = sc.project_visibility(materialize=True)
+    rows = _valid_rows(g)
+    mb = sc.mask_bool()
+    np.testing.assert_array_equal(sc.E.cpu().numpy().reshape(-1, 4, 4)[rows], g["ref_E_aligned"])
+    np.testing.assert_array_equal(mb[rows], g["ref_mask"])
+    xy, z = xy.cpu().numpy(), z.cpu().numpy()
+    np.testing.assert_allclose(xy[rows], g["ref_xy"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(z[rows], g["ref_z"], rtol=RTOL, atol=1e-9)
+    invalid = sorted(set(range(len(g["image_ids"]))) - set(rows))
+    assert invalid and not mb[invalid].any()                       # -inf poses see nothing
+    np.testing.assert_array_equal(sc.valid.cpu().numpy()[invalid], 0)
+    # pad bits beyond n are zero
+    w = sc.mask.cpu().numpy().view(np.uint32)
+    assert int(np.unpackbits(w.view(np.uint8), axis=1, bitorder="little")[:, sc.n:].sum()) == 0
+
+
+def test_golden_pair_relations_and_tables(golden_scannet):
+    from multi_spatialmllm_b200 import engine
+    g = golden_scannet
+    sc = _scene_from_golden(g)
+    ids = [str(s) for s in g["image_ids"]]
+    rel = engine.process_scene_relations(sc, ids)
+    assert len(rel) == len(g["ref_pair_ids"])
+    for (a, b), vals in zip(g["ref_pair_ids"], g["ref_pair_vals"]):
+        r = rel[(str(a), str(b))]
+        assert r["overlap"] == vals[0] or (np.isnan(r["overlap"]) and np.isnan(vals[0]))   # same integers -> same double
+        np.testing.assert_allclose([r["distance"], r["yaw"], r["pitch"]], vals[1:], rtol=1e-12, atol=1e-12)
+    tab = engine.process_scene_visibility(sc, ids)
+    off = g["ref_i2p_off"]
+    assert list(tab["image_to_points"].keys()) == [str(v) for v in g["valid_ids"]]
+    for k, v in enumerate(g["valid_ids"]):
+        assert tab["image_to_points"][str(v)] == g["ref_i2p_flat"][off[k]:off[k + 1]].tolist()
+    assert [len(tab["point_to_images"][p]) for p in range(sc.n)] == g["ref_p2i_cnt"].tolist()
+
+
+def test_golden_point_annotation(golden_scannet):
+    g = golden_scannet
+    sc = _scene_from_golden(g)
+    rows = _valid_rows(g)
+    spot = g["ref_spot"]
+    fr = [rows[int(k)] for k in spot[:, 0]]
+    a = sc.annotate_points(spot[:, 1].astype(np.int32), fr)
+    np.testing.assert_allclose(a["uvz"].cpu().numpy(), spot[:, 2:5], rtol=RTOL)
+    np.testing.assert_array_equal(a["permille"].cpu().numpy(), spot[:, 5:7].astype(np.int32))
+    np.testing.assert_array_equal(a["depth_mm"].cpu().numpy(), spot[:, 7].astype(np.int32))
+    np.testing.assert_array_equal(a["pix"].cpu().numpy(), spot[:, 8:10].astype(np.int32))
+    assert a["visible"].cpu().numpy().all()
+
+
+def test_kth_common_point_selection(golden_scannet):
+    g = golden_scannet
+    sc = _scene_from_golden(g)
+    sc.project_visibility()
+    rows = _valid_rows(g)
+    ref = g["ref_mask"]
+    pairs, sel, expect = [], [], []
+    for i in range(len(rows)):
+        for j in range(len(rows)):
+            if i == j:
+                continue
+            common = og.common_visible_points(np.flatnonzero(ref[i]), np.flatnonzero(ref[j]))
+            ks = sorted({0, len(common) // 2, max(len(common) - 1, 0), len(common), len(common) + 7})
+            for k in ks:
+                pairs.append((rows[i], rows[j])); sel.append(k)
+                expect.append(int(common[k]) if k < len(common) else -1)
+    rec = sc.records_to_numpy(sc.pair_annotate(np.array(pairs, np.int32), np.array(sel, np.uint32), sel_mode=0))
+    np.testing.assert_array_equal(rec["point_id"], expect)
+    got = rec[rec["point_id"] >= 0]
+    assert (got["flags"] == 3).all()            # table <-> re-check invariant (DE-dot:203-213): zero warnings
+    # sel_mode 1: k = floor(r * inter / 2^32)
+    r = np.random.default_rng(0).integers(0, 2**32, len(pairs), dtype=np.uint64).astype(np.uint32)
+    rec1 = sc.records_to_numpy(sc.pair_annotate(np.array(pairs, np.int32), r, sel_mode=1))
+    for (a, b), rv, rr in zip(pairs, r, rec1):
+        common = np.flatnonzero(ref[rows.index(a)] & ref[rows.index(b)])
+        k = (int(rv) * len(common)) >> 32
+        assert rr["point_id"] == (int(common[k]) if len(common) else -1)
+        assert rr["inter"] == len(common)
+
+
+def test_pair_record_integers_match_oracle(golden_scannet):
+    g = golden_scannet
+    H, W = g["image_hw"]
+    sc = _scene_from_golden(g)
+    sc.project_visibility()
+    rows = _valid_rows(g)
+    pairs = np.array([(rows[i], rows[j]) for i in range(len(rows)) for j in range(i + 1, len(rows))], np.int32)
+    rec = sc.records_to_numpy(sc.pair_annotate(pairs, np.full(len(pairs), 3, np.uint32), sel_mode=0))
+    E = g["ref_E_aligned"]
+    pts = g["points"].astype(np.float64)
+    for (a, b), r in zip(pairs, rec):
+        i, j = rows.index(a), rows.index(b)
+        d, _ = og.relative_displacement(E[i], E[j])
+        np.testing.assert_allclose(r["rel_disp"], d, rtol=1e-12, atol=1e-13)
+        assert r["inter"] == int((g["ref_mask"][i] & g["ref_mask"][j]).sum())
+        assert r["uni"] == int((g["ref_mask"][i] | g["ref_mask"][j]).sum())
+        if r["point_id"] < 0:
+            continue
+        for side, (k, f) in enumerate(((i, a), (j, b))):
+            an = og.annotate_point(pts[r["point_id"]], g["K"], E[k], g["depth"][f], H, W)
+            assert an is not None
+            assert list(r["permille"][2 * side:2 * side + 2]) == [an["x_permille"], an["y_permille"]]
+            assert r["depth_mm"][side] == an["depth_mm"]
+            assert tuple(r["pix"][2 * side:2 * side + 2]) == an["pix"]
+
+
+def test_object_counts(golden_scannet):
+    g = golden_scannet
+    sc = _scene_from_golden(g)
+    sc.project_visibility()
+    counts = sc.object_counts().cpu().numpy()
+    mb = sc.mask_bool()
+    for f in range(sc.F):
+        np.testing.assert_array_equal(counts[f], og.object_visible_counts(mb[f], g["instance_ids"], int(g["num_objects"])))
+
+
+def test_zbuffer_matches_oracle(golden_scannet):
+    g = golden_scannet
+    H, W = g["image_hw"]
+    dh, dw = g["depth_hw"]
+    sc = _scene_from_golden(g)
+    zb = sc.render_zbuffer().cpu().numpy()
+    d16 = sc.render_depth(margin_mm=2).cpu().numpy()
+    pts = g["points"].astype(np.float64)
+    for k, f in enumerate(_valid_rows(g)):
+        ref = og.zbuffer_render(pts, g["K"], g["ref_E_aligned"][k], H, W, dh, dw)
+        np.testing.assert_array_equal(zb[f], ref)
+        np.testing.assert_array_equal(d16[f], og.depth_to_u16(ref, 2))
+    # a surface is visible against its own render: every point that won a pixel passes the strict test
+    sc.project_visibility()
+    assert sc.mask_bool().sum() > 0
+
+
+@pytest.mark.parametrize("n,frames,shuffle", [(1, 3, False), (31, 2, False), (1025, 5, True), (50_000, 6, True)])
+def test_random_scenes_vs_oracle(n, frames, shuffle):
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=100 + n, n_points=max(n, 64), n_frames=frames, n_objects=4, shuffle_points=shuffle)
+    pts = s.points[:n]
+    sc = DeviceScene(pts, s.K, s.c2w, axis_align=s.axis_align, image_hw=s.image_hw, depth_hw=s.depth_hw)
+    depth = sc.render_depth(margin_mm=1).cpu().numpy()
+    # perturb: holes + noise so that the depth test is not trivially true
+    rng = np.random.default_rng(n)
+    noisy = depth.astype(np.int64) + rng.integers(-2, 3, depth.shape) * (depth > 0)
+    noisy[rng.random(depth.shape) < 0.05] = 0
+    noisy = np.clip(noisy, 0, 65535).astype(np.uint16)
+    sc.set_depth(noisy)
+    _, xy, z = sc.project_visibility(materialize=True)
+    mb = sc.mask_bool()
+    H, W = s.image_hw
+    for f in range(frames):
+        E = og.aligned_pose(s.axis_align, s.c2w[f])
+        oxy, oz, om = og.frame_visibility(pts.astype(np.float64), s.K, E, noisy[f], H, W)
+        np.testing.assert_array_equal(mb[f], om)
+        np.testing.assert_allclose(xy[f].cpu().numpy(), oxy, rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(z[f].cpu().numpy(), oz, rtol=RTOL, atol=1e-9)
+
+
+def test_generic_intrinsics_path():
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=5, n_points=3000, n_frames=3, n_objects=2)
+    K = s.K.copy()
+    K[0, 1] = 0.7          # skew: not the [fx 0 cx 0] form -> generic 4-term path
+    sc = DeviceScene(s.points, K, s.c2w, axis_align=s.axis_align)
+    sc.render_depth(margin_mm=1)
+    _, xy, z = sc.project_visibility(materialize=True)
+    mb, depth = sc.mask_bool(), sc.depth.cpu().numpy()
+    for f in range(3):
+        E = og.aligned_pose(s.axis_align, s.c2w[f])
+        oxy, oz, om = og.frame_visibility(s.points.astype(np.float64), K, E, depth[f], *s.image_hw)
+        np.testing.assert_array_equal(mb[f], om)
+        np.testing.assert_allclose(xy[f].cpu().numpy(), oxy, rtol=RTOL, atol=1e-6)
+
+
+def test_full_size_properties():
+    """BASELINE config-2 scene size: size-independent properties instead of a CPU oracle pass."""
+    import torch
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=42, n_points=200_000, n_frames=48, n_objects=12)
+    sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids, num_objects=12)
+    sc.render_depth(margin_mm=1)
+    sc.project_visibility()
+    mb = sc.mask_bool()
+    cnt = mb.sum(1)
+    assert (cnt > 1000).all()
+    F = sc.F
+    ij = np.array([(i, j) for i in range(F) for j in range(F)], np.int32)
+    inter, uni, ov = [t.cpu().numpy() for t in sc.pair_overlap(ij)]
+    inter, uni, ov = inter.reshape(F, F), uni.reshape(F, F), ov.reshape(F, F)
+    np.testing.assert_array_equal(inter, inter.T)                      # symmetry
+    np.testing.assert_array_equal(uni, uni.T)
+    np.testing.assert_array_equal(np.diag(inter), cnt)                 # |A&A| = |A|
+    np.testing.assert_array_equal(inter + uni, cnt[:, None] + cnt[None, :])   # inclusion-exclusion
+    np.testing.assert_array_equal(np.diag(ov), 100.0)
+    # three spot frames against the oracle at full size
+    depth = sc.depth.cpu().numpy()
+    for f in (0, 17, 47):
+        E = og.aligned_pose(s.axis_align, s.c2w[f])
+        _, _, om = og.frame_visibility(s.points.astype(np.float64), s.K, E, depth[f], *s.image_hw)
+        np.testing.assert_array_equal(mb[f], om)
+    # object counts sum to the number of visible object points
+    oc = sc.object_counts().cpu().numpy()
+    np.testing.assert_array_equal(oc.sum(1), (mb & (s.instance_ids > 0)[None]).sum(1))
+    # every selected common point passes the re-check in both frames
+    pairs = ij[(ij[:, 0] < ij[:, 1])]
+    rec = sc.records_to_numpy(sc.pair_annotate(pairs, torch.randint(0, 2**31, (len(pairs),), dtype=torch.int32), sel_mode=1))
+    has = rec["point_id"] >= 0
+    assert has.sum() > 0 and (rec["flags"][has] == 3).all()
+    pid = rec["point_id"][has]
+    assert mb[pairs[has, 0], pid].all() and mb[pairs[has, 1], pid].all()
+
+
+def test_tapvid_tracks(golden_tapvid):
+    import ctypes as C
+    import torch
+    from multi_spatialmllm_b200._lib import check, lib
+    g = golden_tapvid
+    T, N, _ = g["tracks_xyz"].shape
+    H, W = [int(v) for v in g["image_hw"]]
+    dev = "cuda:0"
+    tr = torch.from_numpy(g["tracks_xyz"]).to(dev)
+    w2c = torch.from_numpy(g["w2c"].reshape(T, 16)).to(dev)
+    intr = torch.from_numpy(g["fxfycxcy"]).to(dev)
+    world = torch.empty((T, N, 3), dtype=torch.float64, device=dev)
+    uvn = torch.empty((T, N, 2), dtype=torch.float64, device=dev)
+    pm = torch.empty((T, N, 2), dtype=torch.int32, device=dev)
+    ok = torch.empty((T, N), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    check(lib.msp_track_project(tr.data_ptr(), w2c.data_ptr(), intr.data_ptr(), T, N, H, W, world.data_ptr(),
+                                uvn.data_ptr(), pm.data_ptr(), ok.data_ptr(), s))
+    np.testing.assert_allclose(world.cpu().numpy(), g["ref_world"], rtol=1e-12, atol=1e-12)
+    okh = ok.cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(okh, np.isfinite(g["ref_proj"][..., 0]))
+    np.testing.assert_allclose(uvn.cpu().numpy()[okh], g["ref_proj"][okh], rtol=1e-13)
+    np.testing.assert_array_equal(pm.cpu().numpy()[okh], np.round(g["ref_proj"][okh] * 1000).astype(np.int32))
+    # pair displacement vs oracle
+    rng = np.random.default_rng(1)
+    tri = np.stack([rng.integers(0, T, 64), rng.integers(0, T, 64), rng.integers(0, N, 64)], 1).astype(np.int32)
+    trid = torch.from_numpy(tri).to(dev)
+    out = torch.empty((64, 5), dtype=torch.float64, device=dev)
+    check(lib.msp_track_pair_displacement(world.data_ptr(), w2c.data_ptr(), T, N, trid.data_ptr(), 64, out.data_ptr(), s))
+    out = out.cpu().numpy()
+    wr = g["ref_world"]
+    for (f1, f2, p), o in zip(tri, out):
+        d = wr[f2, p] - wr[f1, p]
+        np.testing.assert_allclose(o[0], np.linalg.norm(d), rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(o[1:4], (g["w2c"][f1] @ np.concatenate([d, [0]]))[:3], rtol=1e-10, atol=1e-12)
+        c1, c2 = np.linalg.inv(g["w2c"][f1]), np.linalg.inv(g["w2c"][f2])
+        np.testing.assert_allclose(o[4], np.linalg.norm(c2[:3, 3] - c1[:3, 3]), rtol=1e-10, atol=1e-12)
+
+
+def test_bad_arguments_fail_loudly(golden_scannet):
+    import torch
+    from multi_spatialmllm_b200._lib import MspError
+    sc = _scene_from_golden(golden_scannet)
+    sc.project_visibility()
+    sc.pts = torch.cat([torch.zeros(1, device=sc.device), sc.pts.flatten()])[1:].view(-1, 3)   # 4-byte offset: misaligned
+    with pytest.raises(MspError):
+        sc.project_visibility()
