@@ -80,6 +80,23 @@ def look_at_c2w(eye, target, up=(0.0, 0.0, 1.0)):
     return M
 
 
+def look_at_c2w_batch(eye, target, up=(0.0, 0.0, 1.0)):
+    """Vectorised look_at_c2w: eye, target (F,3) -> (F,4,4)."""
+    eye, target = np.asarray(eye, float), np.asarray(target, float)
+    up = np.broadcast_to(np.asarray(up, float), eye.shape)
+    f = target - eye
+    f = f / np.linalg.norm(f, axis=1, keepdims=True)
+    r = np.cross(f, up)
+    bad = np.linalg.norm(r, axis=1) < 1e-6
+    if bad.any():
+        r[bad] = np.cross(f[bad], np.array([0.0, 1.0, 0.0]))
+    r = r / np.linalg.norm(r, axis=1, keepdims=True)
+    d = np.cross(f, r)
+    M = np.tile(np.eye(4), (eye.shape[0], 1, 1))
+    M[:, :3, 0], M[:, :3, 1], M[:, :3, 2], M[:, :3, 3] = r, d, f, eye
+    return M
+
+
 def make_scene(seed: int, n_points: int, n_frames: int, n_objects: int = 12,
                room=(8.0, 8.0, 3.0), scene_id: str | None = None,
                shuffle_points: bool = False, orbit: bool = False,
@@ -129,20 +146,18 @@ def make_scene(seed: int, n_points: int, n_frames: int, n_objects: int = 12,
     A = np.round(A, 6)
     A_inv = np.linalg.inv(A)
 
-    c2w = np.empty((n_frames, 4, 4))
     ctr = np.array([rx / 2, ry / 2, 1.2])
-    for f in range(n_frames):
-        if orbit:
-            t = 2 * np.pi * f / max(n_frames, 1)
-            eye = ctr + np.array([0.32 * rx * np.cos(t), 0.32 * ry * np.sin(t), 0.3 * np.sin(3 * t)])
-            tgt = ctr + np.array([0.45 * rx * np.cos(t + 2.2), 0.45 * ry * np.sin(t + 2.2), -0.5])
-        else:
-            eye = np.array([rng.uniform(0.8, rx - 0.8), rng.uniform(0.8, ry - 0.8), rng.uniform(0.9, 2.0)])
-            tgt = np.array([rng.uniform(0.0, rx), rng.uniform(0.0, ry), rng.uniform(0.0, 2.0)])
-            if np.linalg.norm(tgt - eye) < 0.5:
-                tgt = ctr
-        c2w[f] = np.round(A_inv @ look_at_c2w(eye, tgt), 6)
-        c2w[f, 3] = [0, 0, 0, 1]
+    if orbit:
+        t = 2 * np.pi * np.arange(n_frames) / max(n_frames, 1)
+        eye = ctr + np.stack([0.32 * rx * np.cos(t), 0.32 * ry * np.sin(t), 0.3 * np.sin(3 * t)], 1)
+        tgt = ctr + np.stack([0.45 * rx * np.cos(t + 2.2), 0.45 * ry * np.sin(t + 2.2), np.full_like(t, -0.5)], 1)
+    else:
+        eye = rng.uniform([0.8, 0.8, 0.9], [rx - 0.8, ry - 0.8, 2.0], size=(n_frames, 3))
+        tgt = rng.uniform([0.0, 0.0, 0.0], [rx, ry, 2.0], size=(n_frames, 3))
+        near = np.linalg.norm(tgt - eye, axis=1) < 0.5
+        tgt[near] = ctr
+    c2w = np.round(A_inv[None] @ look_at_c2w_batch(eye, tgt), 6)
+    c2w[:, 3] = [0, 0, 0, 1]
     if invalid_pose_every:
         c2w[invalid_pose_every - 1::invalid_pose_every] = -np.inf
     sid = scene_id or f"scene{seed:04d}_00"
