@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Benchmark of the MultiSPA geometry hot path (BASELINE.json metric: annotated frame-pair samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                           # the reference's CPU path (oracle port)
+
+Workload at N=1 = BASELINE.json configs[1]: "ScanNet visual_correspondence: 100 scenes x 1k frame-pairs,
+~200k pts/scene, 1xB200", independent-pair model of SURVEY.md §8(d): every pair owns its two frames, so a scene
+carries 2000 frames (poses + 640x480 u16 depth maps) and a step projects 100 x 2000 frames and annotates 100 x 1000
+pairs.  A "step" is one pass over all scenes resident in HBM; with N GPUs every rank owns its own scenes (weak
+scaling, no collective on the data path; one host-side gather of the per-rank manifest sizes).
+
+One JSON line is printed by rank 0.  See DESIGN.md §Measurement for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "annotated_frame_pairs_per_sec"
+UNIT = "pairs/s"
+DEPTH_BYTES = 640 * 480 * 2
+
+
+def algorithmic_bytes_frame(n: int) -> float:
+    """B_frame(N) = 12N (xyz f32) + 614400 (depth u16) + 80 (pose, intrinsics) + N/8 (mask out)."""
+    return 12.0 * n + DEPTH_BYTES + 80.0 + n / 8.0
+
+
+def workload_sizes(args):
+    rng = np.random.default_rng(1000)
+    lo, hi = int(args.points * 0.75), int(args.points * 1.25)
+    return [int(v) for v in rng.integers(lo, hi + 1, args.scenes)]
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi while the timed region runs)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 7:
+                    continue
+                try:
+                    sm.append(float(p[0])); mx.append(float(p[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (the oracle port of the reference's functions), used for cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def _cpu_pair_worker(job):
+    """One worker = one process, like the reference's Pool-by-scene (make_visibility_info.py:151).
+
+    Annotates `n_pairs` independent frame pairs of one synthetic scene with the reference's algorithm
+    (I/O-free variant: depth maps and points are served from RAM).
+    """
+    seed, n_points, n_pairs = job
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(1)
+    except Exception:
+        limiter = None
+    from multi_spatialmllm_b200 import synth
+    from oracle import geometry as og
+    s = synth.make_scene(seed=seed, n_points=n_points, n_frames=2 * n_pairs, n_objects=12)
+    pts = s.points.astype(np.float64)
+    H, W = s.image_hw
+    rng = np.random.default_rng(seed)
+    E = [og.aligned_pose(s.axis_align, s.c2w[f]) for f in range(s.n_frames)]
+    # depth maps are inputs: rendered before the clock starts (on the GPU arm they are rendered at setup too)
+    depth = [og.depth_to_u16(og.zbuffer_render(pts, s.K, E[f], H, W, *s.depth_hw), 1) for f in range(s.n_frames)]
+    t0 = time.perf_counter()
+    done = 0
+    for k in range(n_pairs):
+        a, b = 2 * k, 2 * k + 1
+        _, _, ma = og.frame_visibility(pts, s.K, E[a], depth[a], H, W)          # IH:313-386 per frame
+        _, _, mb = og.frame_visibility(pts, s.K, E[b], depth[b], H, W)
+        og.pair_relations(E[a], E[b], ma, mb)                                       # CFR:176-189
+        og.relative_displacement(E[a], E[b])                                        # CME:185-189
+        common = og.common_visible_points(np.flatnonzero(ma), np.flatnonzero(mb))   # VC-coor:303
+        if len(common):
+            p = int(common[int(rng.integers(0, len(common)))])
+            og.annotate_point(pts[p], s.K, E[a], depth[a], H, W)                    # IH:291-305 + VC-coor:341-344
+            og.annotate_point(pts[p], s.K, E[b], depth[b], H, W)
+        og.object_visible_counts(ma, s.instance_ids, s.num_objects)                 # COV:133-136
+        og.object_visible_counts(mb, s.instance_ids, s.num_objects)
+        done += 1
+    dt = time.perf_counter() - t0
+    if limiter is not None:
+        limiter.unregister() if hasattr(limiter, "unregister") else None
+    return done, dt
+
+
+def run_cpu_sample(n_points: int, pairs_per_worker: int, workers: int, seed0: int = 0):
+    """Wall-clock pairs/s of `workers` processes each annotating `pairs_per_worker` pairs."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    jobs = [(seed0 + w, n_points, pairs_per_worker) for w in range(workers)]
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_noop, range(workers))            # start the interpreters before the clock
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_pair_worker, jobs)
+        wall = time.perf_counter() - t0
+    pairs = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)                       # slowest worker's compute time (setup excluded)
+    return pairs, busy, wall
+
+
+def _cpu_noop(_):
+    import numpy  # noqa: F401
+    from oracle import geometry  # noqa: F401
+    return 0
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    workers = max(1, min(cores, 64))
+    ppw = args.cpu_pairs_per_worker
+    times, pairs_tot = [], 0
+    for it in range(args.warmup + args.steps):
+        pairs, busy, wall = run_cpu_sample(args.points, ppw, workers, seed0=1000 * it)
+        if it >= args.warmup:
+            times.append(busy)
+            pairs_tot += pairs
+    total = float(sum(times))
+    value = pairs_tot / total
+    sample = (f"{workers} processes x {ppw} independent pairs of a {args.points}-point scene per step "
+              f"(oracle port of IH:46-72,337-386 / CFR:102-137 / VC-coor:303-344 / COV:133-136; depth and points in RAM)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, note="CPU arm: bounded sample of the same workload per step"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, note=""):
+    cfg = {
+        "workload": (f"BASELINE configs[1]: ScanNet visual_correspondence, {args.scenes} scenes x {args.pairs_per_scene} "
+                     f"frame-pairs, ~{args.points // 1000}k pts/scene (N~U[0.75,1.25]x), independent-pair model "
+                     f"(2 frames/pair: {2 * args.pairs_per_scene} poses + 640x480 u16 depth maps per scene), "
+                     "points float32 xyz, synthetic room scenes"),
+        "scenes": args.scenes, "pairs_per_scene": args.pairs_per_scene, "points_mean": args.points,
+        "frames_per_scene": 2 * args.pairs_per_scene, "depth": "640x480 u16 (rendered once at setup by msp_zbuffer_render)",
+        "l2": "inputs larger than L2: every step streams all scenes' depth maps + masks (>> 126 MB), no flush needed",
+    }
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from multi_spatialmllm_b200 import _lib, synth  # raises if libmsp.so is missing: no fallback
+    from multi_spatialmllm_b200.engine import DeviceScene
+    from multi_spatialmllm_b200.pipeline import HostScene, PairAnnotator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sizes = workload_sizes(args)
+    P = args.pairs_per_scene
+    F = 2 * P
+    # ---- fit the resident set into HBM (depth dominates: F * 614400 B per scene)
+    free_b, total_b = torch.cuda.mem_get_info()
+    per_scene = F * DEPTH_BYTES + F * (sum(sizes) / len(sizes) / 8 + 64) + 16 * sum(sizes) / len(sizes) + F * 500
+    n_scenes = args.scenes
+    while n_scenes > 1 and n_scenes * per_scene > 0.86 * free_b:
+        n_scenes -= 1
+    sizes = sizes[:n_scenes]
+
+    # ---- setup (untimed): scenes in HBM, depth maps rendered by K2, pair lists, selection words
+    scenes = []
+    t_setup = time.time()
+    for i, n in enumerate(sizes):
+        s = synth.make_scene(seed=rank * 100003 + i, n_points=n, n_frames=F, n_objects=12)
+        sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids,
+                         num_objects=s.num_objects, image_hw=s.image_hw, depth_hw=s.depth_hw, device=dev)
+        sc.render_depth(margin_mm=1)
+        sc.c2w_in, sc.A_in = sc.c2w, torch.from_numpy(s.axis_align.reshape(16)).to(dev)
+        sc.pairs = torch.arange(F, dtype=torch.int32, device=dev).view(P, 2)
+        g = torch.Generator(device=dev); g.manual_seed(1234 + i)
+        sc.sel = torch.randint(-2**31, 2**31 - 1, (P,), dtype=torch.int32, device=dev, generator=g)
+        sc.rec = torch.empty((P, 128), dtype=torch.uint8, device=dev)
+        sc.counts = torch.empty((F, sc.num_objects), dtype=torch.int32, device=dev)
+        sc.mask = torch.zeros((F, sc.stride), dtype=torch.int32, device=dev)
+        scenes.append(sc)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+
+    import ctypes as C
+    from multi_spatialmllm_b200.engine import _ptr, _stream, check, lib
+    launches_per_step = 4 * len(scenes)
+
+    def step(ev=None):
+        for k, sc in enumerate(scenes):
+            st = _stream()
+            check(lib.msp_pose_prepare(_ptr(sc.c2w_in), _ptr(sc.A_in), sc.F, _ptr(sc.E), _ptr(sc.w2c), _ptr(sc.yawpitch),
+                                       _ptr(sc.valid), st))
+            if ev is not None:
+                ev[k][0].record()
+            check(lib.msp_project_visibility(_ptr(sc.pts), sc.n, sc.pts_dtype, sc.K_host.ctypes.data, _ptr(sc.w2c), sc.F,
+                                             _ptr(sc.depth), C.byref(sc.cam), _ptr(sc.mask), sc.stride, None, None, st))
+            if ev is not None:
+                ev[k][1].record()
+            check(lib.msp_object_counts(_ptr(sc.mask), sc.n, sc.stride, sc.F, _ptr(sc.instance_ids), sc.num_objects,
+                                        _ptr(sc.counts), st))
+            check(lib.msp_pair_annotate(_ptr(sc.mask), sc.n, sc.stride, _ptr(sc.pairs), P, _ptr(sc.sel), 1, _ptr(sc.pts),
+                                        sc.pts_dtype, sc.K_host.ctypes.data, _ptr(sc.E), _ptr(sc.w2c), _ptr(sc.yawpitch),
+                                        _ptr(sc.depth), C.byref(sc.cam), _ptr(sc.rec), st))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # sanity: the timed work produces real records
+    r0 = DeviceScene.records_to_numpy(scenes[0].rec)
+    assert (r0["uni"] > 0).all() and (r0["point_id"] >= 0).sum() > 0.5 * P, "step produced empty records"
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in scenes]
+           for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for it in range(args.steps):
+        step(evs[it])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    k1_ms = sum(a.elapsed_time(b) for step_ev in evs for (a, b) in step_ev)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        ns = torch.tensor([len(scenes)], dtype=torch.int64, device=dev)
+        dist.all_reduce(ns, op=dist.ReduceOp.SUM)       # host-side manifest gather stand-in: total scenes done
+        total_scenes = int(ns.item())
+    else:
+        total_scenes = len(scenes)
+    pairs_total = total_scenes * P * args.steps
+    value = pairs_total / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_frame_loop = msp_project_visibility), rank 0's launches
+    k1_bytes = sum(sc.F * algorithmic_bytes_frame(sc.n) for sc in scenes) * args.steps
+    k1_launches = len(scenes) * args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_frame_loop (msp_project_visibility)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes / k1_launches,
+                "avg_launch_ms": k1_ms / k1_launches, "share_of_step": k1_ms / elapsed_ms if world == 1 else None}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args), "roofline": roofline,
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+    }
+    line["config"]["scenes_resident_per_gpu"] = len(scenes)
+    line["config"]["setup_s"] = round(t_setup, 1)
+
+    # ---- e2e through the public API with HOST buffers (rank-local; same metric)
+    if not args.no_e2e:
+        ne = min(args.e2e_scenes, len(scenes))
+        hosts = []
+        for i in range(ne):
+            sc = scenes[i]
+            s = synth.make_scene(seed=rank * 100003 + i, n_points=sc.n, n_frames=F, n_objects=12)
+            hs = HostScene(torch.from_numpy(s.points), s.K, s.axis_align, torch.from_numpy(s.c2w),
+                           sc.depth.cpu(), torch.from_numpy(s.instance_ids), s.num_objects, s.image_hw, s.depth_hw).pin()
+            hs.pairs = sc.pairs.cpu().pin_memory()
+            hs.sel = sc.sel.cpu().pin_memory()
+            hosts.append(hs)
+        ann = PairAnnotator(dev, n_streams=2)
+
+        def e2e_step():
+            hb = db = 0
+            for hs in hosts:
+                h = ann.submit(hs, hs.pairs, hs.sel, sel_mode=1)
+                hb += h["h2d_bytes"]; db += h["d2h_bytes"]
+            out = ann.drain()
+            return hb, db, out
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            hb, db, out = e2e_step()
+        # the public API returns the same records the resident path computed
+        ref = DeviceScene.records_to_numpy(scenes[0].rec)
+        assert np.array_equal(out[0]["records"]["point_id"], ref["point_id"]) and np.array_equal(out[0]["records"]["inter"], ref["inter"])
+        barrier()
+        t0 = time.perf_counter()
+        esteps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(esteps):
+            hb, db, out = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        line["e2e"] = {"value": world * ne * P * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db,
+                       "scenes_per_step": ne, "steps": esteps,
+                       "api": "multi_spatialmllm_b200.pipeline.PairAnnotator.submit/drain on pinned host buffers"}
+        del hosts, ann
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = host_cores()
+        workers = max(1, min(cores, 64))
+        pairs, busy, wall = run_cpu_sample(args.points, args.cpu_pairs_per_worker, workers)
+        line["cpu_baseline"] = {
+            "value": pairs / busy, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": (f"{workers} processes x {args.cpu_pairs_per_worker} independent pairs of a {args.points}-point scene "
+                       f"({pairs} pairs, {busy:.1f} s busy, {wall:.1f} s wall incl. scene setup), NumPy oracle port, data in RAM")}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=100)
+    ap.add_argument("--pairs-per-scene", type=int, default=1000)
+    ap.add_argument("--points", type=int, default=200_000)
+    ap.add_argument("--e2e-scenes", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-pairs-per-worker", type=int, default=24)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
