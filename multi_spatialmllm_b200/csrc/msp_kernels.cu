@@ -4,10 +4,12 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "msp.h"
 #include "msp_device.cuh"
+#include "msp_cull.cuh"
 
 using namespace msp;
 
@@ -532,8 +534,42 @@ extern "C" int msp_pose_prepare(const double* c2w, const double* axis_align, int
   return check_launch("msp_pose_prepare");
 }
 
+// MSP_DISABLE_CULL=1 forces the reference-order kernel for every point (A/B switch used by tests and profiling).
+static bool cull_enabled() {
+  const char* e = getenv("MSP_DISABLE_CULL");
+  return !(e != nullptr && e[0] == '1');
+}
+
 template <int MODE>
 static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool mat, cudaStream_t s) {
+  if (kstd && !mat && cull_enabled()) {
+    // fast path: float32 conservative cull + exact float64 on compacted survivors (msp_cull.cuh)
+    const dim3 grid((unsigned)((p.n + kCullTilePoints - 1) / kCullTilePoints),
+                    (unsigned)((p.F + kCullFramesPerCta - 1) / kCullFramesPerCta));
+    REQUIRE(grid.y <= 65535u, "too many frames in one call");
+    CullParams c{};
+    c.pts = p.pts, c.n = p.n, c.w2c = p.w2c, c.F = p.F, c.depth = p.depth, c.zbuf = p.zbuf;
+    c.depth_stride = p.depth_stride, c.mask = p.mask, c.mask_stride = p.mask_stride, c.K = p.K, c.g = p.g;
+    c.fx = (float)p.K.k[0], c.fy = (float)p.K.k[5], c.cx = (float)p.K.k[2], c.cy = (float)p.K.k[6];
+    c.fw = (float)p.g.image_w, c.fh = (float)p.g.image_h;
+#define MSP_CULL(DT)                                                                                         \
+  {                                                                                                          \
+    constexpr int smem = kCullTilePoints * PtTraits<DT>::kBytes;                                             \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      cudaFuncSetAttribute(k_frame_cull<DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
+    k_frame_cull<DT, MODE><<<grid, kCullThreads, smem, s>>>(c);                                              \
+  }
+    switch (dt) {
+      case 0: MSP_CULL(0) break;
+      case 1: MSP_CULL(1) break;
+      default: MSP_CULL(2) break;
+    }
+#undef MSP_CULL
+    return MSP_OK;
+  }
   const dim3 grid((unsigned)((p.n + kTilePoints - 1) / kTilePoints), (unsigned)((p.F + kFramesPerCta - 1) / kFramesPerCta));
   REQUIRE(grid.y <= 65535u, "too many frames in one call (max 65535*32)");
 #define MSP_LAUNCH(DT, KS, MT) k_frame_loop<DT, KS, MODE, MT><<<grid, kThreads, 0, s>>>(p)

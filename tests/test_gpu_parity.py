@@ -295,3 +295,64 @@ def test_bad_arguments_fail_loudly(golden_scannet):
     sc.pts = torch.cat([torch.zeros(1, device=sc.device), sc.pts.flatten()])[1:].view(-1, 3)   # 4-byte offset: misaligned
     with pytest.raises(MspError):
         sc.project_visibility()
+
+
+def _boundary_points(s, frames, per_frame, rng):
+    """Points back-projected from the image border / the z=0 plane of given frames (float32-rounded):
+    they sit inside or just outside the float32 cull's guard band."""
+    out = []
+    H, W = s.image_hw
+    fx, fy, cx, cy = s.K[0, 0], s.K[1, 1], s.K[0, 2], s.K[1, 2]
+    for f in frames:
+        E = og.aligned_pose(s.axis_align, s.c2w[f])
+        n = per_frame
+        edge = rng.integers(0, 5, n)
+        u = rng.uniform(0, W, n)
+        v = rng.uniform(0, H, n)
+        z = rng.uniform(0.3, 6.0, n)
+        eps = rng.choice([0.0, 1e-9, -1e-9, 1e-6, -1e-6, 1e-4, -1e-4, 1e-2, -1e-2], n)
+        u = np.where(edge == 0, 0.0 + eps, np.where(edge == 1, W + eps, u))
+        v = np.where(edge == 2, 0.0 + eps, np.where(edge == 3, H + eps, v))
+        z = np.where(edge == 4, eps, z)                     # on the camera plane
+        cam = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z, np.ones(n)], 1)
+        out.append((E @ cam.T).T[:, :3])
+    return np.concatenate(out).astype(np.float32)
+
+
+@pytest.mark.parametrize("layout", ["f32x3", "f32x4", "f64x3"])
+def test_cull_path_equals_reference_order_path(layout, monkeypatch):
+    """The float32-cull kernel must give the same bits as the all-float64 kernel, also on points that sit on
+    the frustum boundary, with shuffled point order, ragged N and a frame count that crosses CTA chunks."""
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    rng = np.random.default_rng(77)
+    s = synth.make_scene(seed=9, n_points=120_001, n_frames=70, n_objects=6, shuffle_points=True, invalid_pose_every=33)
+    valid = [f for f in range(70) if og.pose_is_valid(s.c2w[f])]
+    extra = _boundary_points(s, valid[:20], 400, rng)
+    pts = np.concatenate([s.points, extra, np.array([[np.nan, 0, 0], [np.inf, 1, 1], [1e30, 1e30, 1e30]], np.float32)])
+    pts = pts[rng.permutation(len(pts))]
+    if layout == "f32x4":
+        dev_pts = np.concatenate([pts, np.ones((len(pts), 1), np.float32)], 1)
+    elif layout == "f64x3":
+        dev_pts = pts.astype(np.float64) + rng.normal(0, 1e-9, pts.shape)      # not float32-representable
+    else:
+        dev_pts = pts
+    sc = DeviceScene(dev_pts, s.K, s.c2w, axis_align=s.axis_align)
+    monkeypatch.setenv("MSP_DISABLE_CULL", "1")
+    depth_ref = sc.render_depth(margin_mm=1).cpu().numpy()
+    sc.project_visibility()
+    mask_ref = sc.mask.cpu().numpy().copy()
+    monkeypatch.setenv("MSP_DISABLE_CULL", "0")
+    sc.mask.zero_()
+    depth_cull = sc.render_depth(margin_mm=1).cpu().numpy()
+    sc.project_visibility()
+    np.testing.assert_array_equal(depth_cull, depth_ref)
+    np.testing.assert_array_equal(sc.mask.cpu().numpy(), mask_ref)
+    assert np.unpackbits(mask_ref.view(np.uint8)).sum() > 100_000
+    # and both equal the oracle on a few frames
+    mb = sc.mask_bool()
+    p64 = np.asarray(dev_pts[:, :3], dtype=np.float64)
+    for f in (valid[0], valid[7], valid[-1]):
+        E = og.aligned_pose(s.axis_align, s.c2w[f])
+        _, _, om = og.frame_visibility(p64, s.K, E, depth_ref[f], *s.image_hw)
+        np.testing.assert_array_equal(mb[f], om)
