@@ -342,7 +342,7 @@ def main_gpu(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_frame_loop (msp_project_visibility)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_frame_cull (msp_project_visibility)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes / k1_launches,

@@ -422,16 +422,23 @@ __global__ void __launch_bounds__(256) k_object_counts(const uint32_t* __restric
   __syncthreads();
   const uint32_t* row = mask + (int64_t)f * mask_stride;
   const int nwords = (int)((n + 31) / 32);
-  for (int wd = warp; wd < nwords; wd += blockDim.x / 32) {
-    const uint32_t bits = __ldg(row + wd);
-    if (bits == 0) continue;
-    const int64_t pt = (int64_t)wd * 32 + lane;
-    const uint32_t id = (pt < n) ? (uint32_t)__ldg(inst + pt) : 0u;
-    const bool active = ((bits >> lane) & 1u) && id != 0u && id <= (uint32_t)n_objects;
-    const uint32_t m = __ballot_sync(0xffffffffu, active);
-    if (active) {
-      const uint32_t grp = __match_any_sync(m, id);
-      if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[id], (uint32_t)__popc(grp));
+  // each warp fetches 32 mask words with one coalesced load, then visits only the non-empty ones
+  for (int w0 = warp * 32; w0 < nwords; w0 += (blockDim.x / 32) * 32) {
+    const int wd = w0 + lane;
+    const uint32_t mine = (wd < nwords) ? __ldg(row + wd) : 0u;
+    uint32_t nz = __ballot_sync(0xffffffffu, mine != 0u);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const uint32_t bits = __shfl_sync(0xffffffffu, mine, src);
+      const int64_t pt = (int64_t)(w0 + src) * 32 + lane;
+      const uint32_t id = (pt < n) ? (uint32_t)__ldg(inst + pt) : 0u;
+      const bool active = ((bits >> lane) & 1u) && id != 0u && id <= (uint32_t)n_objects;
+      const uint32_t m = __ballot_sync(0xffffffffu, active);
+      if (active) {
+        const uint32_t grp = __match_any_sync(m, id);
+        if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[id], (uint32_t)__popc(grp));
+      }
     }
   }
   __syncthreads();
@@ -550,8 +557,6 @@ static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool m
     CullParams c{};
     c.pts = p.pts, c.n = p.n, c.w2c = p.w2c, c.F = p.F, c.depth = p.depth, c.zbuf = p.zbuf;
     c.depth_stride = p.depth_stride, c.mask = p.mask, c.mask_stride = p.mask_stride, c.K = p.K, c.g = p.g;
-    c.fx = (float)p.K.k[0], c.fy = (float)p.K.k[5], c.cx = (float)p.K.k[2], c.cy = (float)p.K.k[6];
-    c.fw = (float)p.g.image_w, c.fh = (float)p.g.image_h;
 #define MSP_CULL(DT)                                                                                         \
   {                                                                                                          \
     constexpr int smem = kCullTilePoints * PtTraits<DT>::kBytes;                                             \
