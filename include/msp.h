@@ -130,6 +130,12 @@ MSP_API int msp_annotate_points(const void* pts, int64_t n, int32_t pts_dtype, c
                         const uint16_t* depth, const msp_camera* host_cam, double* uvz, int32_t* permille,
                         int32_t* depth_mm, int32_t* pix, uint8_t* visible, void* stream);
 
+/* The reference's two-step API on already projected points (one frame): mode 1 = IH:337-344 (image bounds),
+ * 2 = IH:346-373 (depth test incl. the round/clip index rule, no bounds AND), 3 = IH:375-386 (both).
+ *  xy (n,2), z (n) float64 (z may be NULL for mode 1), depth (depth_h,depth_w) uint16, out (n) uint8. */
+MSP_API int msp_check_visibility(const double* xy, const double* z, int64_t n, const uint16_t* depth,
+                                 const msp_camera* host_cam, int32_t mode, uint8_t* out, void* stream);
+
 /* COV:110-136 for every (frame, object): counts[f*n_objects + o] = |visible_f ∩ {p : instance_ids[p] == o+1}|
  * (instance ids are 1-indexed, 0 = no object, IH:250-261).  instance_ids (n) uint16. */
 MSP_API int msp_object_counts(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, int32_t F,

@@ -410,6 +410,30 @@ __global__ void k_annotate(const AnnotParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// the reference's two-step API: visibility of already projected points (IH:337-386), one thread each
+// ------------------------------------------------------------------------------------------------
+__global__ void k_check_visibility(const double* __restrict__ xy, const double* __restrict__ z, int64_t n,
+                                   const uint16_t* __restrict__ depth, const ImageGeom g, int mode,
+                                   uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Proj pr;
+  pr.u = xy[2 * i], pr.v = xy[2 * i + 1], pr.z = (z != nullptr) ? z[i] : 0.0;
+  bool ok = true;
+  if (mode & 1) ok = in_image(pr, g);  // IH:342-343
+  if (mode & 2) {                      // IH:359-371 — evaluated for every point like the reference (clip, no bounds AND)
+    // np.round(...).astype(int) then clip: out-of-range / non-finite values saturate before the clip
+    const double tx = rint(__dmul_rn(pr.u, g.sx)), ty = rint(__dmul_rn(pr.v, g.sy));
+    // (x86 float64->int64 conversion of NaN, +-inf and |x| >= 2^63 yields INT64_MIN, which the clip turns into 0)
+    const double kBig = 9223372036854775808.0;
+    const int dx = (tx >= kBig) ? 0 : (tx >= (double)g.depth_w) ? g.depth_w - 1 : (tx > 0.0 ? (int)tx : 0);
+    const int dy = (ty >= kBig) ? 0 : (ty >= (double)g.depth_h) ? g.depth_h - 1 : (ty > 0.0 ? (int)ty : 0);
+    ok = ok && depth_test(pr.z, __ldg(depth + (int64_t)dy * g.depth_w + dx), g);
+  }
+  out[i] = ok ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-(frame, object) visible-point counts: one CTA per frame, shared-memory histogram,
 // warp-aggregated by instance id (neighbouring mesh vertices mostly share one)
 // ------------------------------------------------------------------------------------------------
@@ -723,6 +747,19 @@ extern "C" int msp_annotate_points(const void* pts, int64_t n, int32_t pts_dtype
   }
 #undef MSP_ANN
   return check_launch("msp_annotate_points");
+}
+
+extern "C" int msp_check_visibility(const double* xy, const double* z, int64_t n, const uint16_t* depth,
+                                    const msp_camera* host_cam, int32_t mode, uint8_t* out, void* stream) {
+  REQUIRE(n >= 0, "negative size");
+  REQUIRE(mode >= 1 && mode <= 3, "mode must be 1 (bounds), 2 (depth) or 3 (both)");
+  if (n == 0) return MSP_OK;
+  REQUIRE(xy && out, "msp_check_visibility: NULL pointer");
+  REQUIRE(!(mode & 2) || (depth && z), "msp_check_visibility: depth test needs depth and z");
+  ImageGeom g;
+  if (int rc = make_geom(host_cam, &g)) return rc;
+  k_check_visibility<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xy, z, n, depth, g, mode, out);
+  return check_launch("msp_check_visibility");
 }
 
 extern "C" int msp_object_counts(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, int32_t F,
