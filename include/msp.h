@@ -79,6 +79,11 @@ typedef struct msp_pair_record {
 MSP_API int msp_version(void);
 MSP_API const char* msp_last_error(void);
 
+/* Profiling aid: when given a device pointer to two zeroed uint64 counters, the K1/K2 fast path adds
+ * [0] point-frames evaluated in float32 (members of candidate groups) and [1] point-frames re-evaluated by the exact
+ * float64 path.  NULL (default) disables it.  Process-global; not meant for concurrent use. */
+MSP_API int msp_debug_set_cull_stats(unsigned long long* dev_counters2);
+
 /* Per-frame pose prologue.  Replaces IH:113-124 (aligned = axis_align @ c2w), the np.linalg.inv at IH:57,
  * CFR:86-100 (extract_yaw_pitch on the aligned pose) and IH:409-418 (a pose holding inf/nan is invalid).
  *  c2w        (F,16) in       axis_align (16) in, may be NULL (= identity, the reference's align=False)

@@ -37,6 +37,7 @@ _P = C.c_void_p
 _SIGNATURES = {
     "msp_version": (C.c_int, []),
     "msp_last_error": (C.c_char_p, []),
+    "msp_debug_set_cull_stats": (C.c_int, [_P]),
     "msp_pose_prepare": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "msp_project_visibility": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, C.POINTER(MspCamera),
                                          _P, C.c_int64, _P, _P, _P]),

@@ -1,23 +1,29 @@
-// K1/K2 fast path: hierarchical conservative float32 frustum cull + exact float64 evaluation of the
-// survivors, with the depth-map gathers software-pipelined one frame ahead.
+// K1/K2 fast path (msp_project_visibility / msp_zbuffer_render with standard intrinsics).
 //
-// Why this is still bit-exact.  A point can only be visible (or splat into the z-buffer) if it lies in
-// front of the camera and inside the colour image (info_handler.py:342-343,371).  With the standard
-// intrinsics K = [fx 0 cx; 0 fy cy; 0 0 1] and Z > 0 that region is the intersection of four half-spaces
-// of affine forms of the world point p (R0,R1,R2 = rows of w2c, "." includes the translation):
-//     q0 =  i0 =  fx R0.p + cx R2.p          >= 0      (u >= 0)
-//     q1 = -t0 = -fx R0.p + (W - cx) R2.p    >  0      (u <  W)
-//     q2 =  i1 =  fy R1.p + cy R2.p          >= 0      (v >= 0)
-//     q3 = -t1 = -fy R1.p + (H - cy) R2.p    >  0      (v <  H)
-// (q0 >= 0 and q1 > 0 together imply Z > 0.)  The cull evaluates the forms in float32 and rejects a
-// point only if some form is below  -bound_q, where bound_q = 16u * (un-cancelled magnitude of the form
-// over the tile), u = 2^-24, is a rigorous bound on |float32 value - exact value| (coefficient rounding,
-// coordinate rounding for float64 inputs, three FMA roundings: <= 5u).  A whole
-// group of 32 consecutive points is rejected the same way through its bounding box (centre value +
-// |a|.halfsize, evaluated with upward rounding).  Everything that survives — all in-frustum points plus
-// a ~1e-2 pixel guard band — goes through the same exact float64 code as the reference-order kernel
-// (msp_device.cuh), so the masks are identical to it; survivors are compacted per warp through a
-// shared-memory queue so that the float64 work runs on dense warps whatever the point order.
+// Structure per CTA: one tile of 2048 points (TMA bulk copy to SMEM) x one chunk of 64 frames.  Per frame and warp
+// (256 points = 8 groups of 32 consecutive points, lane = point):
+//   A  group classification on 32 lanes (4 half-space forms x 8 group boxes): groups certainly outside are skipped;
+//   B  float32 evaluation of the remaining groups' points with rigorous error bounds: certainly outside -> done,
+//      certainly inside with a certain depth pixel -> the depth gather is issued, anything uncertain -> exact queue;
+//   C  float32 depth comparison with bounds (certain -> mask bit via ballot, uncertain -> exact queue);
+//   D  the (rare) queued lanes are re-evaluated by the exact float64 reference-order code (msp_device.cuh).
+// A float32 decision is only ever taken when the bound proves that the exact float64 reference arithmetic takes
+// the same decision, so the output is bit-identical to the all-float64 kernel (k_frame_loop).  Proof sketch, u=2^-24:
+//
+//   Coordinates are re-centred on the tile centre c (x' = fl(x - c)); each affine form F(p) = a.p + d of
+//   DESIGN.md §3 is evaluated as fl(a0 x' + fl(a1 y' + fl(a2 z' + d'))), d' = fl32(a.c + d) formed in float64.
+//   Sources of error: coefficient rounding 1u, re-centring 1u, float64->float32 input rounding 1u, three FMA
+//   roundings 3u on the a.x' part; 1u + 3u on d'.  Hence |F^ - F| <= 6u (A_F + |d'_F|), A_F = sum |a_k| ext_k,
+//   ext_k = max_tile |x'_k|.  We use B_F = 8u (A_F + |d'_F|) + 2^-46 M_F (M_F = un-cancelled magnitude, covering the
+//   float64 evaluation of d' and the reference's own float64 rounding).  Forms (already scaled to depth pixels,
+//   sx = dw/W, sy = dh/H):  I0 = sx(fx X + cx Z),  Q1 = dw Z - I0,  I1 = sy(fy Y + cy Z),  Q3 = dh Z - I1,  Z.
+//   In the image  <=>  I0 >= 0, Q1 > 0, I1 >= 0, Q3 > 0 (these imply Z > 0).  With B >= every form's bound
+//   (derived forms Q1,Q3 included) and m = min(I0^,Q1^,I1^,Q3^):  m < -B  => outside in the reference;
+//   m >= 2B => inside with margin >= B (enough to survive the reference's final division rounding);  else queue.
+//   Pixel: t^ = I0^ * rcp(Z^) approximates the reference's u*sx within  dt = Ct1 * rcp(Z^) + Ct0,
+//   Ct1 >= 1.01 (B_I0 + dw B_Z),  Ct0 >= 8u dw + 1e-9;  rint(t^) is the reference's pixel iff |t^ - rint(t^)| <= 1/2 - dt.
+//   Depth: d^ = fl(float(raw) * 0.001f) is within 2.1u d of raw*0.001;  Z^ within B_Z of the reference's z;
+//   visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^), certainly false when Z^ >= d^ + (B_Z + 6u d^).
 #pragma once
 
 #include "msp_device.cuh"
@@ -30,13 +36,15 @@ constexpr int kCullPtsPerLane = 8;                             // 8 groups of 32
 constexpr int kCullWarpPoints = 32 * kCullPtsPerLane;          // 256
 constexpr int kCullTilePoints = kCullWarps * kCullWarpPoints;  // 2048
 constexpr int kCullFramesPerCta = 64;
-constexpr int kCullPending = 4;  // survivor rounds per frame whose depth gather stays in flight across one frame
 
-struct CullFrameConsts {  // per (CTA tile, frame); 96 bytes
-  float form[4][4];       // {a0,a1,a2,d} of q0..q3 above, rounded to float32
-  float bound[4];         // survive needs q >= -bound
+struct CullFrameConsts {  // per (CTA tile, frame); 128 bytes, all relative to the tile centre
+  float box[4][4];        // I0, Q1, I1, Q3 as {a0,a1,a2,d'} for the group-box test
+  float fz[4];            // Z form {a0,a1,a2,d'}
+  float B;                // common bound of the four in-image forms
+  float Bz;               // bound of the Z form
+  float ct1, ct0;         // pixel-index guard band  dt = ct1 * rcp(Z) + ct0
   int std_frame;          // bottom row of w2c is exactly [0,0,0,1]
-  int pad[3];
+  int pad[7];
 };
 
 struct CullParams {
@@ -51,6 +59,7 @@ struct CullParams {
   int64_t mask_stride;
   Intrinsics K;
   ImageGeom g;
+  unsigned long long* stats;  // optional: [0] lanes evaluated in float32, [1] lanes sent to the exact path
 };
 
 template <int DT>
@@ -73,6 +82,11 @@ __device__ __forceinline__ int f2ord(float f) {
   return i ^ ((i >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // max relative error 2^-23 (PTX ISA), covered by ct0/ct1
+  return r;
+}
 
 template <int DT, int MODE /*0 = visibility mask, 1 = z-buffer splat*/>
 __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams p) {
@@ -80,8 +94,8 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
   __shared__ __align__(16) double s_w[kCullFramesPerCta * 16];
   __shared__ __align__(16) CullFrameConsts s_c[kCullFramesPerCta];
   __shared__ uint32_t s_words[kCullWarps][kCullPtsPerLane];
-  __shared__ uint8_t s_q[2][kCullWarps][kCullWarpPoints];
-  __shared__ uint32_t s_max[3];
+  __shared__ uint8_t s_q[kCullWarps][kCullWarpPoints];
+  __shared__ int s_red[9];  // ordered-int min xyz, max xyz, then uint max |x'|,|y'|,|z'|
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,7 +111,9 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
-    s_max[0] = s_max[1] = s_max[2] = 0u;
+    s_red[0] = s_red[1] = s_red[2] = 0x7fffffff;
+    s_red[3] = s_red[4] = s_red[5] = (int)0x80000000;
+    s_red[6] = s_red[7] = s_red[8] = 0;
   }
   if (tid < kCullWarps * kCullPtsPerLane) (&s_words[0][0])[tid] = 0u;
   __syncthreads();
@@ -110,184 +126,242 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
   mbar_wait(&s_bar, 0);
   __syncthreads();
 
-  // ---- this lane's points (float32 registers), the tile maxima of |x|,|y|,|z| and the group boxes
+  // ---- this lane's points, tile box -> centre, re-centred coordinates, group boxes, extents
   float px[kCullPtsPerLane], py[kCullPtsPerLane], pz[kCullPtsPerLane];
   const float qnan = __int_as_float(0x7fc00000);
   const float finf = __int_as_float(0x7f800000);
-  float mx = 0.f, my = 0.f, mz = 0.f;
-  float bcx = qnan, bcy = qnan, bcz = qnan, bhx = 0.f, bhy = 0.f, bhz = 0.f;  // box of group (lane & 7)
-#pragma unroll
-  for (int j = 0; j < kCullPtsPerLane; ++j) {
-    const int idx = warp * kCullWarpPoints + j * 32 + lane;
-    px[j] = py[j] = pz[j] = qnan;  // slots beyond the tile never survive the cull
+  {
     float lx = finf, ly = finf, lz = finf, hx = -finf, hy = -finf, hz = -finf;
-    if (idx < cnt) {
-      load_point_f32<DT>(s_pts, idx, px[j], py[j], pz[j]);
-      if (isfinite(px[j]) && isfinite(py[j]) && isfinite(pz[j])) {
-        lx = hx = px[j], ly = hy = py[j], lz = hz = pz[j];
-        mx = fmaxf(mx, fabsf(px[j])), my = fmaxf(my, fabsf(py[j])), mz = fmaxf(mz, fabsf(pz[j]));
+#pragma unroll
+    for (int j = 0; j < kCullPtsPerLane; ++j) {
+      const int idx = warp * kCullWarpPoints + j * 32 + lane;
+      px[j] = py[j] = pz[j] = qnan;  // slots beyond the tile and non-finite points: every comparison on them is false
+      if (idx < cnt) {
+        float x, y, z;
+        load_point_f32<DT>(s_pts, idx, x, y, z);
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+          px[j] = x, py[j] = y, pz[j] = z;
+          lx = fminf(lx, x), ly = fminf(ly, y), lz = fminf(lz, z);
+          hx = fmaxf(hx, x), hy = fmaxf(hy, y), hz = fmaxf(hz, z);
+        }
       }
     }
-    const float gx0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lx))), gx1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hx)));
-    const float gy0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(ly))), gy1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hy)));
-    const float gz0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lz))), gz1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hz)));
-    if ((lane & 7) == j) {
-      // centre / half size with the half size rounded up so that [c-h, c+h] certainly contains the group
-      // (for float64 inputs the float32 roundings of the coordinates are covered by the extra 2^-22 |c| term)
-      const float k1 = 1.0f + 2.384185791015625e-07f, k2 = 4.76837158203125e-07f;  // 1+2^-22, 2^-21
-      bcx = 0.5f * (gx0 + gx1), bcy = 0.5f * (gy0 + gy1), bcz = 0.5f * (gz0 + gz1);
-      bhx = __fmaf_ru(0.5f * (gx1 - gx0), k1, k2 * fmaxf(fabsf(gx0), fabsf(gx1)));
-      bhy = __fmaf_ru(0.5f * (gy1 - gy0), k1, k2 * fmaxf(fabsf(gy0), fabsf(gy1)));
-      bhz = __fmaf_ru(0.5f * (gz1 - gz0), k1, k2 * fmaxf(fabsf(gz0), fabsf(gz1)));
-      // an empty group has inf - inf = NaN in its centre: every test on it is false, the group is skipped
+    const int ox0 = __reduce_min_sync(0xffffffffu, f2ord(lx)), ox1 = __reduce_max_sync(0xffffffffu, f2ord(hx));
+    const int oy0 = __reduce_min_sync(0xffffffffu, f2ord(ly)), oy1 = __reduce_max_sync(0xffffffffu, f2ord(hy));
+    const int oz0 = __reduce_min_sync(0xffffffffu, f2ord(lz)), oz1 = __reduce_max_sync(0xffffffffu, f2ord(hz));
+    if (lane == 0) {
+      atomicMin(&s_red[0], ox0), atomicMin(&s_red[1], oy0), atomicMin(&s_red[2], oz0);
+      atomicMax(&s_red[3], ox1), atomicMax(&s_red[4], oy1), atomicMax(&s_red[5], oz1);
     }
   }
+  __syncthreads();
+  // tile centre (any finite value works for correctness; an empty tile gets 0)
+  float tcx = 0.5f * (ord2f(s_red[0]) + ord2f(s_red[3])), tcy = 0.5f * (ord2f(s_red[1]) + ord2f(s_red[4])),
+        tcz = 0.5f * (ord2f(s_red[2]) + ord2f(s_red[5]));
+  if (!isfinite(tcx) || !isfinite(tcy) || !isfinite(tcz)) tcx = tcy = tcz = 0.f;
+  float bcx = qnan, bcy = qnan, bcz = qnan, bhx = 0.f, bhy = 0.f, bhz = 0.f;  // box of group (lane & 7), re-centred
   {
-    const uint32_t ux = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
-    const uint32_t uy = __reduce_max_sync(0xffffffffu, __float_as_uint(my));
-    const uint32_t uz = __reduce_max_sync(0xffffffffu, __float_as_uint(mz));
-    if (lane == 0) atomicMax(&s_max[0], ux), atomicMax(&s_max[1], uy), atomicMax(&s_max[2], uz);
+    float ex = 0.f, ey = 0.f, ez = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCullPtsPerLane; ++j) {
+      px[j] -= tcx, py[j] -= tcy, pz[j] -= tcz;  // NaN stays NaN
+      const bool ok = px[j] == px[j];
+      ex = fmaxf(ex, fabsf(px[j])), ey = fmaxf(ey, fabsf(py[j])), ez = fmaxf(ez, fabsf(pz[j]));  // fmaxf ignores NaN
+      const float lx = ok ? px[j] : finf, ly = ok ? py[j] : finf, lz = ok ? pz[j] : finf;
+      const float hx = ok ? px[j] : -finf, hy = ok ? py[j] : -finf, hz = ok ? pz[j] : -finf;
+      const float gx0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lx))), gx1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hx)));
+      const float gy0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(ly))), gy1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hy)));
+      const float gz0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lz))), gz1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hz)));
+      if ((lane & 7) == j) {
+        // centre / half size with the half size rounded up so that [c-h, c+h] certainly contains the group's x'
+        const float k1 = 1.0f + 2.384185791015625e-07f, k2 = 4.76837158203125e-07f;  // 1+2^-22, 2^-21
+        bcx = 0.5f * (gx0 + gx1), bcy = 0.5f * (gy0 + gy1), bcz = 0.5f * (gz0 + gz1);
+        bhx = __fmaf_ru(0.5f * (gx1 - gx0), k1, k2 * fmaxf(fabsf(gx0), fabsf(gx1)));
+        bhy = __fmaf_ru(0.5f * (gy1 - gy0), k1, k2 * fmaxf(fabsf(gy0), fabsf(gy1)));
+        bhz = __fmaf_ru(0.5f * (gz1 - gz0), k1, k2 * fmaxf(fabsf(gz0), fabsf(gz1)));
+        // an empty group has inf - inf = NaN in its centre: every test on it is false, the group is skipped
+      }
+    }
+    const uint32_t ux = __reduce_max_sync(0xffffffffu, __float_as_uint(ex));
+    const uint32_t uy = __reduce_max_sync(0xffffffffu, __float_as_uint(ey));
+    const uint32_t uz = __reduce_max_sync(0xffffffffu, __float_as_uint(ez));
+    if (lane == 0) atomicMax(&s_red[6], (int)ux), atomicMax(&s_red[7], (int)uy), atomicMax(&s_red[8], (int)uz);
   }
   __syncthreads();
 
-  // ---- per-frame float32 forms and rigorous error bounds (one thread per frame)
+  // ---- per-frame float32 forms and rigorous error bounds (one thread per frame, float64 arithmetic)
   if (tid < nf) {
     const double* w = s_w + tid * 16;
-    // a float64 coordinate rounded to float32 may exceed the true |x| by one ulp at most; inflate anyway
-    const double kUp = 1.0 + 1.1920928955078125e-07;
-    const double ax = (double)__uint_as_float(s_max[0]) * kUp, ay = (double)__uint_as_float(s_max[1]) * kUp,
-                 az = (double)__uint_as_float(s_max[2]) * kUp;
-    CullFrameConsts c;
-    double S[3];
+    const double kUp = 1.0 + 2.4e-07;  // extents: cover the rounding of x' itself and of float64 inputs
+    const double ext[3] = {(double)__int_as_float(s_red[6]) * kUp, (double)__int_as_float(s_red[7]) * kUp,
+                           (double)__int_as_float(s_red[8]) * kUp};
+    const double tc[3] = {(double)tcx, (double)tcy, (double)tcz};
+    const double fx = p.K.k[0], cx = p.K.k[2], fy = p.K.k[5], cy = p.K.k[6];
+    const double sx = p.g.sx, sy = p.g.sy, dw = (double)p.g.depth_w, dh = (double)p.g.depth_h;
+    // float64 coefficient rows of I0, Q1, I1, Q3, Z on original coordinates (k = 0..2 linear, 3 = constant)
+    double A[5][4], M[5];
+    double mag[3];  // un-cancelled |row| . (|c| + ext) + |t| of the three w2c rows
 #pragma unroll
     for (int r = 0; r < 3; ++r)
-      S[r] = fabs(w[4 * r]) * ax + fabs(w[4 * r + 1]) * ay + fabs(w[4 * r + 2]) * az + fabs(w[4 * r + 3]);
-    const double fx = p.K.k[0], cx = p.K.k[2], fy = p.K.k[5], cy = p.K.k[6], W = p.g.img_w, H = p.g.img_h;
+      mag[r] = fabs(w[4 * r]) * (fabs(tc[0]) + ext[0]) + fabs(w[4 * r + 1]) * (fabs(tc[1]) + ext[1]) +
+               fabs(w[4 * r + 2]) * (fabs(tc[2]) + ext[2]) + fabs(w[4 * r + 3]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      c.form[0][k] = __double2float_rn(fx * w[k] + cx * w[8 + k]);
-      c.form[1][k] = __double2float_rn(-fx * w[k] + (W - cx) * w[8 + k]);
-      c.form[2][k] = __double2float_rn(fy * w[4 + k] + cy * w[8 + k]);
-      c.form[3][k] = __double2float_rn(-fy * w[4 + k] + (H - cy) * w[8 + k]);
+      A[0][k] = sx * (fx * w[k] + cx * w[8 + k]);
+      A[2][k] = sy * (fy * w[4 + k] + cy * w[8 + k]);
+      A[4][k] = w[8 + k];
+      A[1][k] = dw * w[8 + k] - A[0][k];
+      A[3][k] = dh * w[8 + k] - A[2][k];
     }
-    const double u16 = 16.0 * 5.9604644775390625e-08;  // 16 * 2^-24
-    // un-cancelled magnitudes: they dominate sum_k |a_qk| m_k + |d_q| and also the reference's own float64 rounding
-    c.bound[0] = __double2float_ru(u16 * (fabs(fx) * S[0] + fabs(cx) * S[2]));
-    c.bound[1] = __double2float_ru(u16 * (fabs(fx) * S[0] + (fabs(W) + fabs(cx)) * S[2]));
-    c.bound[2] = __double2float_ru(u16 * (fabs(fy) * S[1] + fabs(cy) * S[2]));
-    c.bound[3] = __double2float_ru(u16 * (fabs(fy) * S[1] + (fabs(H) + fabs(cy)) * S[2]));
-    // NaN / inf poses give NaN forms -> nothing survives, which is what the exact path returns for them too
-    c.std_frame = (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
-    if (!c.std_frame && isfinite(S[0] + S[1] + S[2])) {
-      // perspective row present: the forms are not the image-plane tests, keep every point
+    M[0] = fabs(sx) * (fabs(fx) * mag[0] + fabs(cx) * mag[2]);
+    M[2] = fabs(sy) * (fabs(fy) * mag[1] + fabs(cy) * mag[2]);
+    M[4] = mag[2];
+    M[1] = dw * mag[2] + M[0];
+    M[3] = dh * mag[2] + M[2];
+    CullFrameConsts c;
+    const double u = 5.9604644775390625e-08, tiny = 1.4210854715202004e-14;  // 2^-24, 2^-46
+    double Bf[5];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        c.form[q][0] = c.form[q][1] = c.form[q][2] = c.form[q][3] = 0.f;
-        c.bound[q] = finf;
-      }
+    for (int q = 0; q < 5; ++q) {
+      const double dprime = A[q][0] * tc[0] + A[q][1] * tc[1] + A[q][2] * tc[2] + A[q][3];
+      const double Aext = fabs(A[q][0]) * ext[0] + fabs(A[q][1]) * ext[1] + fabs(A[q][2]) * ext[2];
+      Bf[q] = 8.0 * u * (Aext + fabs(dprime)) + tiny * M[q];
+      float* dst = (q < 4) ? c.box[q] : c.fz;
+      dst[0] = __double2float_rn(A[q][0]), dst[1] = __double2float_rn(A[q][1]), dst[2] = __double2float_rn(A[q][2]);
+      dst[3] = __double2float_rn(dprime);
     }
-    c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    // Q1 and Q3 are *derived* in the point loop as fl(dw Z^ - I0^): their error is B_I0 + dw B_Z + one rounding
+    // (the final FMA rounding u |Q^| <= u (A_ext + |d'|)(1+..) <= 0.13 Bf of the directly evaluated form)
+    const double bq1 = 1.01 * (Bf[0] + dw * Bf[4]) + 0.13 * Bf[1];
+    const double bq3 = 1.01 * (Bf[2] + dh * Bf[4]) + 0.13 * Bf[3];
+    const double B = fmax(fmax(Bf[0], Bf[2]), fmax(fmax(Bf[1], Bf[3]), fmax(bq1, bq3)));
+    c.B = __double2float_ru(B);
+    c.Bz = __double2float_ru(Bf[4]);
+    c.ct1 = __double2float_ru(1.01 * fmax(Bf[0] + dw * Bf[4], Bf[2] + dh * Bf[4]));
+    c.ct0 = __double2float_ru(8.0 * u * fmax(dw, dh) + 1e-9);
+    c.std_frame = (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
+    if (!c.std_frame && isfinite(B)) {
+      // perspective row present: the forms are not the image-plane tests — send every point to the exact path
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c.box[q][0] = c.box[q][1] = c.box[q][2] = c.box[q][3] = 0.f;
+      c.B = finf;
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) c.pad[i] = 0;
     s_c[tid] = c;
   }
   __syncthreads();
 
   const int64_t word0 = (int64_t)blockIdx.x * (kCullTilePoints / 32) + warp * kCullPtsPerLane;
   const uint32_t lt = (1u << lane) - 1u;
+  const bool word_ok = (lane < kCullPtsPerLane) && (word0 + lane < p.mask_stride);
+  uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;
+  const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h;
+  const float fdw1 = fdw - 1.0f, fdh1 = fdh - 1.0f;
   constexpr uint32_t kNoCand = 0xffffffffu;
-  double zp[kCullPending];
-  uint32_t rawp[kCullPending];
-#pragma unroll
-  for (int r = 0; r < kCullPending; ++r) zp[r] = 0.0, rawp[r] = kNoCand;
-  uint32_t prev_total = 0;
+  unsigned int st_f32 = 0, st_exact = 0;
 
-  for (int fi = 0; fi <= nf; ++fi) {
-    const int cur = fi & 1;
-    uint32_t total = 0;
-    // ---- stage A(fi): float32 cull, first per group box, then per point of the groups that are left
-    if (fi < nf) {
-      const CullFrameConsts& c = s_c[fi];
-      const int q = lane >> 3;
-      const float4 a = *reinterpret_cast<const float4*>(c.form[q]);
-      const float v = fmaf(a.x, bcx, fmaf(a.y, bcy, fmaf(a.z, bcz, a.w)));
-      const float r = __fmaf_ru(fabsf(a.x), bhx, __fmaf_ru(fabsf(a.y), bhy, __fmul_ru(fabsf(a.z), bhz)));
-      const uint32_t gb = __ballot_sync(0xffffffffu, __fadd_ru(v, r) >= -c.bound[q]);
-      const uint32_t gm = gb & (gb >> 8) & (gb >> 16) & (gb >> 24) & 0xffu;
-      if (gm != 0u) {
-        const float4 a0 = *reinterpret_cast<const float4*>(c.form[0]);
-        const float4 a1 = *reinterpret_cast<const float4*>(c.form[1]);
-        const float4 a2 = *reinterpret_cast<const float4*>(c.form[2]);
-        const float4 a3 = *reinterpret_cast<const float4*>(c.form[3]);
-        const float4 nb = *reinterpret_cast<const float4*>(c.bound);
-#pragma unroll
-        for (int j = 0; j < kCullPtsPerLane; ++j) {
-          if (gm & (1u << j)) {  // warp-uniform
-            const float q0 = fmaf(a0.x, px[j], fmaf(a0.y, py[j], fmaf(a0.z, pz[j], a0.w)));
-            const float q1 = fmaf(a1.x, px[j], fmaf(a1.y, py[j], fmaf(a1.z, pz[j], a1.w)));
-            const float q2 = fmaf(a2.x, px[j], fmaf(a2.y, py[j], fmaf(a2.z, pz[j], a2.w)));
-            const float q3 = fmaf(a3.x, px[j], fmaf(a3.y, py[j], fmaf(a3.z, pz[j], a3.w)));
-            const bool surv = (q0 >= -nb.x) & (q1 >= -nb.y) & (q2 >= -nb.z) & (q3 >= -nb.w);
-            const uint32_t b = __ballot_sync(0xffffffffu, surv);
-            if (surv) s_q[cur][warp][total + __popc(b & lt)] = (uint8_t)((j << 5) | lane);
-            total += __popc(b);
-          }
-        }
-      }
-    }
-    __syncwarp();
+  for (int fi = 0; fi < nf; ++fi) {
+    const CullFrameConsts& c = s_c[fi];
+    const int64_t f = f0 + fi;
+    uint32_t myword = 0;  // lane j (< 8) ends up holding mask word j of this warp
+    uint32_t nq = 0;      // lanes queued for the exact path
 
-    // ---- consume(fi-1): the gathers issued one iteration ago have had stage A(fi) to land
-    if (MODE == 0 && fi > 0) {
-      const int64_t f = f0 + fi - 1;
-#pragma unroll
-      for (int r = 0; r < kCullPending; ++r) {
-        if (rawp[r] != kNoCand) {
-          if (depth_test(zp[r], (uint16_t)rawp[r], p.g)) {
-            const uint32_t code = s_q[cur ^ 1][warp][r * 32 + lane];
-            atomicOr(&s_words[warp][code >> 5], 1u << (code & 31));
-          }
-        }
-      }
-      __syncwarp();
-      if (lane < kCullPtsPerLane) {
-        const uint32_t wv = s_words[warp][lane];
-        s_words[warp][lane] = 0u;
-        if (word0 + lane < p.mask_stride) p.mask[f * p.mask_stride + word0 + lane] = wv;
-      }
-      __syncwarp();
-    }
+    // ---- A: group boxes against the four half-spaces (lane = form q x group g)
+    const float4 a = *reinterpret_cast<const float4*>(c.box[lane >> 3]);
+    const float B = c.B;
+    const float v = fmaf(a.x, bcx, fmaf(a.y, bcy, fmaf(a.z, bcz, a.w)));
+    const float r = __fmaf_ru(fabsf(a.x), bhx, __fmaf_ru(fabsf(a.y), bhy, __fmul_ru(fabsf(a.z), bhz)));
+    const uint32_t gb = __ballot_sync(0xffffffffu, __fadd_ru(v, r) >= -B);
+    const uint32_t gm = gb & (gb >> 8) & (gb >> 16) & (gb >> 24) & 0xffu;
 
-    // ---- stage B(fi): exact float64 projection of the compacted survivors; depth gathers are only issued here
-    if (fi < nf) {
-      const double* w = s_w + fi * 16;
-      const bool fstd = s_c[fi].std_frame != 0;
-      const int64_t f = f0 + fi;
+    if (gm != 0u) {
+      const float4 a0 = *reinterpret_cast<const float4*>(c.box[0]);
+      const float4 a2 = *reinterpret_cast<const float4*>(c.box[2]);
+      const float4 az = *reinterpret_cast<const float4*>(c.fz);
+      const float B2 = B + B, ct1 = c.ct1, half_ct0 = 0.5f - c.ct0, Bz = c.Bz;
+      const uint16_t* dm = p.depth + f * p.depth_stride;
+      // two halves of four groups keep the number of gathers in flight per lane (and registers) bounded
 #pragma unroll
-      for (int r = 0; r < kCullPending; ++r) {
-        rawp[r] = kNoCand;
-        const uint32_t t = r * 32 + lane;
-        if (t < total) {
-          const uint32_t code = s_q[cur][warp][t];
-          const int idx = warp * kCullWarpPoints + (int)(code >> 5) * 32 + (int)(code & 31);
-          double x, y, z;
-          PtTraits<DT>::load(s_pts, idx, x, y, z);
-          const Proj pr = fstd ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
-          if (in_image(pr, p.g) && pr.z > 0.0) {
-            const int di = depth_index(pr, p.g);
-            if (MODE == 0) {
-              rawp[r] = ldg_u16_nc(p.depth + f * p.depth_stride + di);
-              zp[r] = pr.z;
-            } else {
-              atomicMin(reinterpret_cast<unsigned int*>(p.zbuf + f * p.depth_stride) + di,
-                        __float_as_uint(__double2float_rn(pr.z)));
+      for (int h = 0; h < kCullPtsPerLane; h += 4) {
+      uint32_t raw[4];
+      float zf[4];
+      // ---- B: float32 projection of the candidate groups; depth gathers issued for the certain lanes
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = h + jj;
+        raw[jj] = kNoCand;
+        zf[jj] = 0.f;
+        if (gm & (1u << j)) {  // warp-uniform
+          const float I0 = fmaf(a0.x, px[j], fmaf(a0.y, py[j], fmaf(a0.z, pz[j], a0.w)));
+          const float I1 = fmaf(a2.x, px[j], fmaf(a2.y, py[j], fmaf(a2.z, pz[j], a2.w)));
+          const float Z = fmaf(az.x, px[j], fmaf(az.y, py[j], fmaf(az.z, pz[j], az.w)));
+          const float Q1 = fmaf(fdw, Z, -I0), Q3 = fmaf(fdh, Z, -I1);
+          const float m = fminf(fminf(I0, Q1), fminf(I1, Q3));  // NaN inputs propagate a NaN only if all are NaN...
+          const bool bad = !(I0 == I0) | !(I1 == I1) | !(Z == Z);  // ...so test NaN explicitly
+          bool unc = false;
+          if (!bad) {
+            if (m >= B2) {  // certainly inside the image and in front of the camera
+              const float rz = rcp_approx(Z);
+              const float tx = I0 * rz, ty = I1 * rz;
+              const float ix = rintf(tx), iy = rintf(ty);
+              const float e = fmaxf(fabsf(tx - ix), fabsf(ty - iy));
+              if (e <= fmaf(-ct1, rz, half_ct0)) {  // the reference rounds to the same depth pixel
+                const float di = fmaf(fminf(iy, fdh1), fdw, fminf(ix, fdw1));
+                if (MODE == 0) {
+                  raw[jj] = ldg_u16_nc(dm + (int)di);
+                  zf[jj] = Z;
+                } else {
+                  // z-buffer value is float32(z_ref): only certain if the float64 z rounds like this float32 Z — it
+                  // does not in general, so the splat always takes the exact path (still culled/skipped above)
+                  unc = true;
+                }
+              } else {
+                unc = true;
+              }
+            } else if (!(m < -B)) {
+              unc = true;  // inside the guard band of a frustum plane
             }
           }
+          const uint32_t bu = __ballot_sync(0xffffffffu, unc);
+          if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
+          nq += __popc(bu);
         }
       }
-      // more than kCullPending*32 survivors in this warp's 256 points: finish the rest synchronously
-      for (uint32_t t0 = kCullPending * 32; t0 < total; t0 += 32) {
+      // ---- C: depth comparison in float32 with bounds
+      if (MODE == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = h + jj;
+          if (gm & (1u << j)) {
+            bool vis = false, unc = false;
+            if (raw[jj] != kNoCand) {
+              const float d = (float)raw[jj] * (float)p.g.depth_scale;
+              const float mz = fmaf(3.6e-7f, d, Bz);  // 6u d + B_Z: d^ is within 2.1u d of raw*0.001, plus the rounding of d -/+ mz
+              vis = zf[jj] < d - mz;
+              unc = !vis && !(zf[jj] >= d + mz);
+            }
+            const uint32_t bv = __ballot_sync(0xffffffffu, vis);
+            const uint32_t bu = __ballot_sync(0xffffffffu, unc);
+            if (lane == j) myword = bv;
+            if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
+            nq += __popc(bu);
+          }
+        }
+      }
+      }  // halves
+      if (p.stats != nullptr) st_f32 += __popc(gm) , st_exact += (lane == 0) ? nq : 0;
+    }
+
+    // ---- D: exact float64 reference-order evaluation of the queued lanes (rare)
+    if (nq != 0u) {
+      __syncwarp();
+      const double* w = s_w + fi * 16;
+      const bool fstd = c.std_frame != 0;
+      for (uint32_t t0 = 0; t0 < nq; t0 += 32) {
         const uint32_t t = t0 + lane;
-        if (t < total) {
-          const uint32_t code = s_q[cur][warp][t];
+        if (t < nq) {
+          const uint32_t code = s_q[warp][t];
           const int j = code >> 5, sl = code & 31;
           const int idx = warp * kCullWarpPoints + j * 32 + sl;
           double x, y, z;
@@ -304,9 +378,18 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
           }
         }
       }
+      __syncwarp();
+      if (MODE == 0 && lane < kCullPtsPerLane) {
+        myword |= s_words[warp][lane];
+        s_words[warp][lane] = 0u;
+      }
+      __syncwarp();
     }
-    prev_total = total;
-    (void)prev_total;
+    if (MODE == 0 && word_ok) mask_ptr[(int64_t)fi * p.mask_stride] = myword;
+  }
+  if (p.stats != nullptr) {
+    atomicAdd(p.stats + 0, (unsigned long long)st_f32);
+    atomicAdd(p.stats + 1, (unsigned long long)st_exact);
   }
 }
 

@@ -32,6 +32,7 @@ static int check_launch(const char* what) {
     if (!(cond)) return fail(MSP_EINVAL, msg);          \
   } while (0)
 
+static unsigned long long* g_cull_stats = nullptr;  // device pointer set by msp_debug_set_cull_stats (profiling aid)
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------------
@@ -553,6 +554,10 @@ static int make_geom(const msp_camera* c, ImageGeom* g) {
 }
 
 extern "C" int msp_version(void) { return MSP_VERSION; }
+extern "C" int msp_debug_set_cull_stats(unsigned long long* dev_counters2) {
+  g_cull_stats = dev_counters2;
+  return MSP_OK;
+}
 extern "C" const char* msp_last_error(void) { return g_err; }
 
 extern "C" int msp_pose_prepare(const double* c2w, const double* axis_align, int32_t F, double* E_out, double* w2c_out,
@@ -581,6 +586,7 @@ static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool m
     CullParams c{};
     c.pts = p.pts, c.n = p.n, c.w2c = p.w2c, c.F = p.F, c.depth = p.depth, c.zbuf = p.zbuf;
     c.depth_stride = p.depth_stride, c.mask = p.mask, c.mask_stride = p.mask_stride, c.K = p.K, c.g = p.g;
+    c.stats = g_cull_stats;
 #define MSP_CULL(DT)                                                                                         \
   {                                                                                                          \
     constexpr int smem = kCullTilePoints * PtTraits<DT>::kBytes;                                             \
