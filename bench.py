@@ -270,7 +270,7 @@ def main_gpu(args):
 
     import ctypes as C
     from multi_spatialmllm_b200.engine import _ptr, _stream, check, lib
-    launches_per_step = 4 * len(scenes)
+    launches_per_step = 3 * len(scenes)      # pose prologue, K1 (+fused object counts), pair stage
 
     def step(ev=None):
         for k, sc in enumerate(scenes):
@@ -279,12 +279,12 @@ def main_gpu(args):
                                        _ptr(sc.valid), st))
             if ev is not None:
                 ev[k][0].record()
-            check(lib.msp_project_visibility(_ptr(sc.pts), sc.n, sc.pts_dtype, sc.K_host.ctypes.data, _ptr(sc.w2c), sc.F,
-                                             _ptr(sc.depth), C.byref(sc.cam), _ptr(sc.mask), sc.stride, None, None, st))
+            # masks + per-(frame, object) counts in one pass over the points (K1 with fused COV counting)
+            check(lib.msp_project_visibility_objects(_ptr(sc.pts), sc.n, sc.pts_dtype, sc.K_host.ctypes.data, _ptr(sc.w2c),
+                                                     sc.F, _ptr(sc.depth), C.byref(sc.cam), _ptr(sc.mask), sc.stride,
+                                                     _ptr(sc.instance_ids), sc.num_objects, _ptr(sc.counts), st))
             if ev is not None:
                 ev[k][1].record()
-            check(lib.msp_object_counts(_ptr(sc.mask), sc.n, sc.stride, sc.F, _ptr(sc.instance_ids), sc.num_objects,
-                                        _ptr(sc.counts), st))
             check(lib.msp_pair_annotate(_ptr(sc.mask), sc.n, sc.stride, _ptr(sc.pairs), P, _ptr(sc.sel), 1, _ptr(sc.pts),
                                         sc.pts_dtype, sc.K_host.ctypes.data, _ptr(sc.E), _ptr(sc.w2c), _ptr(sc.yawpitch),
                                         _ptr(sc.depth), C.byref(sc.cam), _ptr(sc.rec), st))
@@ -342,7 +342,7 @@ def main_gpu(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_frame_cull (msp_project_visibility)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_frame_cull (msp_project_visibility_objects)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes / k1_launches,

@@ -102,6 +102,15 @@ MSP_API int msp_project_visibility(const void* pts, int64_t n, int32_t pts_dtype
                            int32_t F, const uint16_t* depth, const msp_camera* host_cam, uint32_t* mask_bits,
                            int64_t mask_stride_words, double* xy_out, double* z_out, void* stream);
 
+/* msp_project_visibility fused with msp_object_counts (COV:110-136): the masks AND counts[f*n_objects + o] in one
+ * pass over the points (falls back to the two separate kernels when n_objects > 63, the intrinsics are not the
+ * standard form, or n_objects == 0).  counts (F,n_objects) is overwritten. */
+MSP_API int msp_project_visibility_objects(const void* pts, int64_t n, int32_t pts_dtype, const double* host_K16,
+                                           const double* w2c, int32_t F, const uint16_t* depth,
+                                           const msp_camera* host_cam, uint32_t* mask_bits, int64_t mask_stride_words,
+                                           const uint16_t* instance_ids, int32_t n_objects, uint32_t* counts,
+                                           void* stream);
+
 /* Z-buffer depth render — NOT in the reference: per frame, per depth pixel, the minimum
  * float32(z) over points with z > 0 inside the colour image (IH:342-343), binned with the reference's own
  * index rule (IH:359-366).  zbuf (F,depth_h,depth_w) float32 is overwritten (+inf where empty). */

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "msp_pose_prepare": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "msp_project_visibility": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, C.POINTER(MspCamera),
                                          _P, C.c_int64, _P, _P, _P]),
+    "msp_project_visibility_objects": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, C.POINTER(MspCamera),
+                                                 _P, C.c_int64, _P, C.c_int32, _P, _P]),
     "msp_zbuffer_render": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, C.POINTER(MspCamera), _P, _P]),
     "msp_depth_to_u16": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, _P]),
     "msp_pair_overlap": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),

@@ -36,6 +36,7 @@ constexpr int kCullPtsPerLane = 8;                             // 8 groups of 32
 constexpr int kCullWarpPoints = 32 * kCullPtsPerLane;          // 256
 constexpr int kCullTilePoints = kCullWarps * kCullWarpPoints;  // 2048
 constexpr int kCullFramesPerCta = 64;
+constexpr int kCullMaxObjects = 63;  // fused object counting keeps a (64 frames x 64 ids) histogram in SMEM
 
 struct CullFrameConsts {  // per (CTA tile, frame); 128 bytes, all relative to the tile centre
   float box[4][4];        // I0, Q1, I1, Q3 as {a0,a1,a2,d'} for the group-box test
@@ -59,6 +60,9 @@ struct CullParams {
   int64_t mask_stride;
   Intrinsics K;
   ImageGeom g;
+  const uint16_t* inst;       // optional (n): 1-indexed instance ids for fused per-(frame, object) counts
+  uint32_t* counts;           // optional (F, n_objects), zeroed by the caller; accumulated with atomics
+  int32_t n_objects;          // <= kCullMaxObjects when counts != NULL
   unsigned long long* stats;  // optional: [0] lanes evaluated in float32, [1] lanes sent to the exact path
 };
 
@@ -88,8 +92,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-template <int DT, int MODE /*0 = visibility mask, 1 = z-buffer splat*/>
+template <int DT, int MODE /*0 = visibility mask, 1 = z-buffer splat*/, bool COUNT = false>
 __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams p) {
+  __shared__ uint32_t s_cnt[COUNT ? kCullFramesPerCta * (kCullMaxObjects + 1) : 1];
   extern __shared__ __align__(128) unsigned char s_pts[];  // kCullTilePoints * PtTraits<DT>::kBytes (dynamic)
   __shared__ __align__(16) double s_w[kCullFramesPerCta * 16];
   __shared__ __align__(16) CullFrameConsts s_c[kCullFramesPerCta];
@@ -116,6 +121,8 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
     s_red[6] = s_red[7] = s_red[8] = 0;
   }
   if (tid < kCullWarps * kCullPtsPerLane) (&s_words[0][0])[tid] = 0u;
+  if (COUNT)
+    for (int i = tid; i < kCullFramesPerCta * (kCullMaxObjects + 1); i += kCullThreads) s_cnt[i] = 0u;
   __syncthreads();
   if (tid == 0) {
     mbar_arrive_expect_tx(&s_bar, bulk);
@@ -125,6 +132,27 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
   for (int i = tid; i < nf * 16; i += kCullThreads) s_w[i] = p.w2c[(int64_t)f0 * 16 + i];
   mbar_wait(&s_bar, 0);
   __syncthreads();
+
+  // ---- fused object counting: instance id of each of this lane's points; groups whose 32 ids agree are counted
+  //      with one popcount (neighbouring mesh vertices mostly belong to one object, compute_object_visibility.py:110-136)
+  uint32_t ids_lo = 0, ids_hi = 0, ids_lo2 = 0, ids_hi2 = 0;  // 8 x u16 packed
+  uint32_t uni_mask = 0;                                       // bit j: group j has one id (kept in gid of lane j)
+  uint32_t gid = 0;
+  if (COUNT) {
+#pragma unroll
+    for (int j = 0; j < kCullPtsPerLane; ++j) {
+      const int idx = warp * kCullWarpPoints + j * 32 + lane;
+      uint32_t id = (idx < cnt) ? (uint32_t)__ldg(p.inst + base + idx) : 0u;
+      if (id > (uint32_t)p.n_objects) id = 0u;
+      const uint32_t first = __shfl_sync(0xffffffffu, id, 0);
+      // slots beyond the tile never become visible, so they may be ignored when testing uniformity
+      const bool same = __all_sync(0xffffffffu, id == first || idx >= cnt);
+      if (same) uni_mask |= 1u << j;
+      if (lane == j) gid = first;
+      const uint32_t sh = (uint32_t)(j & 1) * 16u;
+      if (j < 2) ids_lo |= id << sh; else if (j < 4) ids_hi |= id << sh; else if (j < 6) ids_lo2 |= id << sh; else ids_hi2 |= id << sh;
+    }
+  }
 
   // ---- this lane's points, tile box -> centre, re-centred coordinates, group boxes, extents
   float px[kCullPtsPerLane], py[kCullPtsPerLane], pz[kCullPtsPerLane];
@@ -255,7 +283,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
   const int64_t word0 = (int64_t)blockIdx.x * (kCullTilePoints / 32) + warp * kCullPtsPerLane;
   const uint32_t lt = (1u << lane) - 1u;
   const bool word_ok = (lane < kCullPtsPerLane) && (word0 + lane < p.mask_stride);
-  uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;
+  uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;  // advanced by one row per frame
   const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h;
   const float fdw1 = fdw - 1.0f, fdh1 = fdh - 1.0f;
   constexpr uint32_t kNoCand = 0xffffffffu;
@@ -324,8 +352,10 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
             }
           }
           const uint32_t bu = __ballot_sync(0xffffffffu, unc);
-          if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
-          nq += __popc(bu);
+          if (bu != 0u) {  // rare, warp-uniform
+            if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
+            nq += __popc(bu);
+          }
         }
       }
       // ---- C: depth comparison in float32 with bounds
@@ -344,8 +374,10 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
             const uint32_t bv = __ballot_sync(0xffffffffu, vis);
             const uint32_t bu = __ballot_sync(0xffffffffu, unc);
             if (lane == j) myword = bv;
-            if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
-            nq += __popc(bu);
+            if (bu != 0u) {
+              if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
+              nq += __popc(bu);
+            }
           }
         }
       }
@@ -385,7 +417,37 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
       }
       __syncwarp();
     }
-    if (MODE == 0 && word_ok) mask_ptr[(int64_t)fi * p.mask_stride] = myword;
+    if (MODE == 0) {
+      if (word_ok) *mask_ptr = myword;
+      mask_ptr += p.mask_stride;
+      if (COUNT) {
+        // lanes 0..7 hold the final words; uniform groups: one shared-memory add per non-empty word
+        const bool mine_uni = (lane < kCullPtsPerLane) && ((uni_mask >> lane) & 1u);
+        if (mine_uni && myword != 0u && gid != 0u) atomicAdd(&s_cnt[fi * (kCullMaxObjects + 1) + gid], (uint32_t)__popc(myword));
+        uint32_t mixed = __ballot_sync(0xffffffffu, (lane < kCullPtsPerLane) && !mine_uni && myword != 0u);
+        while (mixed) {  // groups that straddle an object boundary (rare): aggregate by id within the warp
+          const int j = __ffs(mixed) - 1;
+          mixed &= mixed - 1;
+          const uint32_t wv = __shfl_sync(0xffffffffu, myword, j);
+          const uint32_t pack = (j < 2) ? ids_lo : (j < 4) ? ids_hi : (j < 6) ? ids_lo2 : ids_hi2;
+          const uint32_t id = (pack >> ((uint32_t)(j & 1) * 16u)) & 0xffffu;
+          const bool act = ((wv >> lane) & 1u) && id != 0u;
+          const uint32_t am = __ballot_sync(0xffffffffu, act);
+          if (act) {
+            const uint32_t grp = __match_any_sync(am, id);
+            if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * (kCullMaxObjects + 1) + id], (uint32_t)__popc(grp));
+          }
+        }
+      }
+    }
+  }
+  if (COUNT) {
+    __syncthreads();
+    for (int i = tid; i < nf * p.n_objects; i += kCullThreads) {
+      const int fr = i / p.n_objects, o = i - fr * p.n_objects;
+      const uint32_t v = s_cnt[fr * (kCullMaxObjects + 1) + o + 1];
+      if (v != 0u) atomicAdd(p.counts + (int64_t)(f0 + fr) * p.n_objects + o, v);
+    }
   }
   if (p.stats != nullptr) {
     atomicAdd(p.stats + 0, (unsigned long long)st_f32);

@@ -96,6 +96,9 @@ struct FrameLoopParams {
   double* z;
   Intrinsics K;
   ImageGeom g;
+  const uint16_t* inst;  // fused object counting (fast path only)
+  uint32_t* counts;
+  int32_t n_objects;
 };
 
 enum { MODE_VIS = 0, MODE_ZBUF = 1 };
@@ -587,24 +590,31 @@ static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool m
     c.pts = p.pts, c.n = p.n, c.w2c = p.w2c, c.F = p.F, c.depth = p.depth, c.zbuf = p.zbuf;
     c.depth_stride = p.depth_stride, c.mask = p.mask, c.mask_stride = p.mask_stride, c.K = p.K, c.g = p.g;
     c.stats = g_cull_stats;
-#define MSP_CULL(DT)                                                                                         \
+    c.inst = p.inst, c.counts = p.counts, c.n_objects = p.n_objects;
+    const bool count = (MODE == MODE_VIS) && p.counts != nullptr;
+#define MSP_CULL_LAUNCH(DT, CNT)                                                                             \
   {                                                                                                          \
     constexpr int smem = kCullTilePoints * PtTraits<DT>::kBytes;                                             \
     static bool attr_set = false;                                                                            \
     if (!attr_set) {                                                                                         \
-      cudaFuncSetAttribute(k_frame_cull<DT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+      cudaFuncSetAttribute(k_frame_cull<DT, MODE, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
       attr_set = true;                                                                                       \
     }                                                                                                        \
-    k_frame_cull<DT, MODE><<<grid, kCullThreads, smem, s>>>(c);                                              \
+    k_frame_cull<DT, MODE, CNT><<<grid, kCullThreads, smem, s>>>(c);                                         \
   }
+#define MSP_CULL(DT)                                      \
+  if (MODE == MODE_VIS && count) MSP_CULL_LAUNCH(DT, true) \
+  else MSP_CULL_LAUNCH(DT, false)
     switch (dt) {
       case 0: MSP_CULL(0) break;
       case 1: MSP_CULL(1) break;
       default: MSP_CULL(2) break;
     }
+#undef MSP_CULL_LAUNCH
 #undef MSP_CULL
     return MSP_OK;
   }
+  REQUIRE(p.counts == nullptr, "internal: fused counting needs the fast path");
   const dim3 grid((unsigned)((p.n + kTilePoints - 1) / kTilePoints), (unsigned)((p.F + kFramesPerCta - 1) / kFramesPerCta));
   REQUIRE(grid.y <= 65535u, "too many frames in one call (max 65535*32)");
 #define MSP_LAUNCH(DT, KS, MT) k_frame_loop<DT, KS, MODE, MT><<<grid, kThreads, 0, s>>>(p)
@@ -644,6 +654,38 @@ extern "C" int msp_project_visibility(const void* pts, int64_t n, int32_t pts_dt
   p.K = make_intr(K16);
   if (int rc = launch_frame_loop<MODE_VIS>(p, pts_dtype, k_is_std(K16), xy_out != nullptr, (cudaStream_t)stream)) return rc;
   return check_launch("msp_project_visibility");
+}
+
+extern "C" int msp_project_visibility_objects(const void* pts, int64_t n, int32_t pts_dtype, const double* K16,
+                                              const double* w2c, int32_t F, const uint16_t* depth,
+                                              const msp_camera* host_cam, uint32_t* mask_bits, int64_t mask_stride_words,
+                                              const uint16_t* instance_ids, int32_t n_objects, uint32_t* counts,
+                                              void* stream) {
+  REQUIRE(n >= 0 && F >= 0 && n_objects >= 0, "negative size");
+  REQUIRE(n_objects <= 8191, "n_objects must be <= 8191");
+  if (F == 0) return MSP_OK;
+  REQUIRE(n_objects == 0 || (instance_ids && counts), "msp_project_visibility_objects: NULL instance_ids / counts");
+  const bool fused = n_objects > 0 && n_objects <= kCullMaxObjects && n > 0 && K16 != nullptr && k_is_std(K16) && cull_enabled();
+  if (!fused) {  // same result in two launches
+    if (int rc = msp_project_visibility(pts, n, pts_dtype, K16, w2c, F, depth, host_cam, mask_bits, mask_stride_words,
+                                        nullptr, nullptr, stream)) return rc;
+    return msp_object_counts(mask_bits, n, mask_stride_words, F, instance_ids, n_objects, counts, stream);
+  }
+  REQUIRE(pts_dtype >= 0 && pts_dtype <= 2, "pts_dtype must be 0, 1 or 2");
+  REQUIRE(pts && w2c && depth && mask_bits, "msp_project_visibility_objects: NULL pointer");
+  REQUIRE(aligned16(pts) && aligned16(mask_bits), "pts and mask_bits must be 16-byte aligned");
+  REQUIRE(mask_stride_words % 4 == 0 && mask_stride_words >= (n + 31) / 32, "mask_stride_words must be a multiple of 4 and >= ceil(n/32)");
+  FrameLoopParams p{};
+  if (int rc = make_geom(host_cam, &p.g)) return rc;
+  p.pts = pts, p.n = n, p.w2c = w2c, p.F = F, p.depth = depth, p.zbuf = nullptr;
+  p.depth_stride = (int64_t)host_cam->depth_h * host_cam->depth_w;
+  p.mask = mask_bits, p.mask_stride = mask_stride_words;
+  p.K = make_intr(K16);
+  p.inst = instance_ids, p.counts = counts, p.n_objects = n_objects;
+  if (cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)F * (size_t)n_objects, (cudaStream_t)stream) != cudaSuccess)
+    return check_launch("msp_project_visibility_objects(memset)");
+  if (int rc = launch_frame_loop<MODE_VIS>(p, pts_dtype, true, false, (cudaStream_t)stream)) return rc;
+  return check_launch("msp_project_visibility_objects");
 }
 
 extern "C" int msp_zbuffer_render(const void* pts, int64_t n, int32_t pts_dtype, const double* K16, const double* w2c,

@@ -144,6 +144,18 @@ class DeviceScene:
                                          _ptr(xy), _ptr(z), _stream()), "msp_project_visibility")
         return (self.mask, xy, z) if materialize else self.mask
 
+    def project_visibility_objects(self):
+        """Masks and per-(frame, object) visible counts in one pass (msp_project_visibility_objects)."""
+        assert self.depth is not None and self.instance_ids is not None and self.num_objects > 0
+        if self.mask is None:
+            self.mask = torch.zeros((self.F, self.stride), dtype=torch.int32, device=self.device)
+        counts = torch.empty((self.F, self.num_objects), dtype=torch.int32, device=self.device)
+        check(lib.msp_project_visibility_objects(_ptr(self.pts), self.n, self.pts_dtype, self.K_host.ctypes.data,
+                                                 _ptr(self.w2c), self.F, _ptr(self.depth), C.byref(self.cam),
+                                                 _ptr(self.mask), self.stride, _ptr(self.instance_ids), self.num_objects,
+                                                 _ptr(counts), _stream()), "msp_project_visibility_objects")
+        return self.mask, counts
+
     def mask_bool(self) -> np.ndarray:
         """(F,N) bool on the host — the reference's in_bounds mask per frame (IH:386)."""
         w = self.mask.cpu().numpy().view(np.uint32)

@@ -63,13 +63,16 @@ class PairAnnotator:
                              instance_ids=scene.instance_ids, num_objects=scene.num_objects,
                              image_hw=scene.image_hw, depth_hw=scene.depth_hw, depth_scale=scene.depth_scale,
                              device=self.device)
-            sc.project_visibility()
+            cnt = None
+            if scene.instance_ids is not None and scene.num_objects > 0:
+                _, cnt = sc.project_visibility_objects()
+            else:
+                sc.project_visibility()
             rec = sc.pair_annotate(pairs, sel, sel_mode)
             rec_h = torch.empty((P, 128), dtype=torch.uint8, pin_memory=True)
             rec_h.copy_(rec, non_blocking=True)
             cnt_h = None
-            if scene.instance_ids is not None and scene.num_objects > 0:
-                cnt = sc.object_counts()
+            if cnt is not None:
                 cnt_h = torch.empty(tuple(cnt.shape), dtype=torch.int32, pin_memory=True)
                 cnt_h.copy_(cnt, non_blocking=True)
         h = {"records": rec_h, "object_counts": cnt_h, "scene": sc, "h2d_bytes": scene.h2d_bytes() + P * 12,

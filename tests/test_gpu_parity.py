@@ -148,6 +148,31 @@ def test_object_counts(golden_scannet):
     mb = sc.mask_bool()
     for f in range(sc.F):
         np.testing.assert_array_equal(counts[f], og.object_visible_counts(mb[f], g["instance_ids"], int(g["num_objects"])))
+    mask_before = sc.mask.cpu().numpy().copy()
+    _, fused = sc.project_visibility_objects()            # K1 with the counting fused in
+    np.testing.assert_array_equal(fused.cpu().numpy(), counts)
+    np.testing.assert_array_equal(sc.mask.cpu().numpy(), mask_before)
+
+
+def test_fused_object_counts_mixed_groups_and_fallback():
+    """Instance ids that change inside 32-point groups, ids above n_objects, and the >63-object fallback."""
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=21, n_points=70_003, n_frames=67, n_objects=9, shuffle_points=False)
+    rng = np.random.default_rng(5)
+    for n_obj, ids in ((9, s.instance_ids.copy()), (40, rng.integers(0, 45, s.n_points).astype(np.uint16)),
+                       (100, rng.integers(0, 101, s.n_points).astype(np.uint16))):
+        ids[::977] = 60000                                  # out-of-range ids are ignored (treated as "no object")
+        sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=ids, num_objects=n_obj)
+        sc.render_depth(1)
+        _, fused = sc.project_visibility_objects()
+        sep = sc.object_counts().cpu().numpy()
+        np.testing.assert_array_equal(fused.cpu().numpy(), sep)
+        mb = sc.mask_bool()
+        good = np.where(ids <= n_obj, ids, 0)
+        for f in (0, 33, 66):
+            np.testing.assert_array_equal(sep[f], og.object_visible_counts(mb[f], good, n_obj))
+        assert sep.sum() > 0
 
 
 def test_zbuffer_matches_oracle(golden_scannet):
@@ -239,6 +264,7 @@ def test_full_size_properties():
     # object counts sum to the number of visible object points
     oc = sc.object_counts().cpu().numpy()
     np.testing.assert_array_equal(oc.sum(1), (mb & (s.instance_ids > 0)[None]).sum(1))
+    np.testing.assert_array_equal(sc.project_visibility_objects()[1].cpu().numpy(), oc)
     # every selected common point passes the re-check in both frames
     pairs = ij[(ij[:, 0] < ij[:, 1])]
     rec = sc.records_to_numpy(sc.pair_annotate(pairs, torch.randint(0, 2**31, (len(pairs),), dtype=torch.int32), sel_mode=1))
