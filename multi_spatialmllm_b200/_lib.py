@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsp.so")
+LIB_PATH = os.environ.get("MSP_LIB", os.path.join(_HERE, "libmsp.so"))   # MSP_LIB: alternative build (tuning experiments)
 
 MSP_PTS_F32X3, MSP_PTS_F32X4, MSP_PTS_F64X3 = 0, 1, 2
 

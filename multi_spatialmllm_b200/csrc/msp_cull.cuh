@@ -35,8 +35,17 @@ constexpr int kCullWarps = kCullThreads / 32;
 constexpr int kCullPtsPerLane = 8;                             // 8 groups of 32 points per warp
 constexpr int kCullWarpPoints = 32 * kCullPtsPerLane;          // 256
 constexpr int kCullTilePoints = kCullWarps * kCullWarpPoints;  // 2048
-constexpr int kCullFramesPerCta = 64;
-constexpr int kCullMaxObjects = 63;  // fused object counting keeps a (64 frames x 64 ids) histogram in SMEM
+#ifndef MSP_CULL_FRAMES
+#define MSP_CULL_FRAMES 64
+#endif
+constexpr int kCullFramesPerCta = MSP_CULL_FRAMES;
+constexpr int kCullMaxObjects = 63;
+#ifndef MSP_CULL_MINBLOCKS
+#define MSP_CULL_MINBLOCKS 4
+#endif
+#ifndef MSP_CULL_W_SMEM
+#define MSP_CULL_W_SMEM 0  // 1: keep the chunk's float64 poses in SMEM for the exact path, 0: read them from global
+#endif  // fused object counting keeps a (64 frames x 64 ids) histogram in SMEM
 
 struct CullFrameConsts {  // per (CTA tile, frame); 128 bytes, all relative to the tile centre
   float box[4][4];        // I0, Q1, I1, Q3 as {a0,a1,a2,d'} for the group-box test
@@ -93,10 +102,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 template <int DT, int MODE /*0 = visibility mask, 1 = z-buffer splat*/, bool COUNT = false>
-__global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams p) {
-  __shared__ uint32_t s_cnt[COUNT ? kCullFramesPerCta * (kCullMaxObjects + 1) : 1];
+__global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull(const CullParams p) {
+  // per (frame, id) visible counts of this tile: <= 2048 each, two 16-bit counters per word
+  constexpr int kCntWords = (kCullMaxObjects + 1) / 2;
+  __shared__ uint32_t s_cnt[COUNT ? kCullFramesPerCta * kCntWords : 1];
   extern __shared__ __align__(128) unsigned char s_pts[];  // kCullTilePoints * PtTraits<DT>::kBytes (dynamic)
+#if MSP_CULL_W_SMEM
   __shared__ __align__(16) double s_w[kCullFramesPerCta * 16];
+#endif
   __shared__ __align__(16) CullFrameConsts s_c[kCullFramesPerCta];
   __shared__ uint32_t s_words[kCullWarps][kCullPtsPerLane];
   __shared__ uint8_t s_q[kCullWarps][kCullWarpPoints];
@@ -122,14 +135,18 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
   }
   if (tid < kCullWarps * kCullPtsPerLane) (&s_words[0][0])[tid] = 0u;
   if (COUNT)
-    for (int i = tid; i < kCullFramesPerCta * (kCullMaxObjects + 1); i += kCullThreads) s_cnt[i] = 0u;
+    for (int i = tid; i < kCullFramesPerCta * kCntWords; i += kCullThreads) s_cnt[i] = 0u;
   __syncthreads();
   if (tid == 0) {
     mbar_arrive_expect_tx(&s_bar, bulk);
     if (bulk) bulk_g2s(s_pts, gsrc, bulk, &s_bar);
   }
   if (tid < (int)(bytes - bulk)) s_pts[bulk + tid] = gsrc[bulk + tid];
+#if MSP_CULL_W_SMEM
   for (int i = tid; i < nf * 16; i += kCullThreads) s_w[i] = p.w2c[(int64_t)f0 * 16 + i];
+#else
+  const double* s_w = p.w2c + (int64_t)f0 * 16;  // read through L2 by the per-frame prep threads and the rare exact path
+#endif
   mbar_wait(&s_bar, 0);
   __syncthreads();
 
@@ -188,6 +205,9 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
         tcz = 0.5f * (ord2f(s_red[2]) + ord2f(s_red[5]));
   if (!isfinite(tcx) || !isfinite(tcy) || !isfinite(tcz)) tcx = tcy = tcz = 0.f;
   float bcx = qnan, bcy = qnan, bcz = qnan, bhx = 0.f, bhy = 0.f, bhz = 0.f;  // box of group (lane & 7), re-centred
+  // From here on the tile buffer holds the RE-CENTRED float32 coordinates (x',y',z' packed, NaN for empty slots);
+  // the original coordinates are only needed by the rare exact path, which reads them from global memory (L2).
+  float* s_rel = reinterpret_cast<float*>(s_pts);
   {
     float ex = 0.f, ey = 0.f, ez = 0.f;
 #pragma unroll
@@ -215,7 +235,12 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
     const uint32_t uz = __reduce_max_sync(0xffffffffu, __float_as_uint(ez));
     if (lane == 0) atomicMax(&s_red[6], (int)ux), atomicMax(&s_red[7], (int)uy), atomicMax(&s_red[8], (int)uz);
   }
-  __syncthreads();
+  __syncthreads();  // every thread has read its original coordinates: the buffer may now be overwritten
+#pragma unroll
+  for (int j = 0; j < kCullPtsPerLane; ++j) {
+    const int idx = warp * kCullWarpPoints + j * 32 + lane;
+    s_rel[3 * idx + 0] = px[j], s_rel[3 * idx + 1] = py[j], s_rel[3 * idx + 2] = pz[j];
+  }
 
   // ---- per-frame float32 forms and rigorous error bounds (one thread per frame, float64 arithmetic)
   if (tid < nf) {
@@ -286,8 +311,44 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
   uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;  // advanced by one row per frame
   const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h;
   const float fdw1 = fdw - 1.0f, fdh1 = fdh - 1.0f;
-  constexpr uint32_t kNoCand = 0xffffffffu;
   unsigned int st_f32 = 0, st_exact = 0;
+
+  // float32 evaluation of one group's point on this lane (branch-free; see the header comment for the bounds)
+  struct Lane32 {
+    float zf;
+    uint32_t raw;
+    bool go, unc;
+  };
+  auto eval32 = [&](int j, const float4& a0, const float4& a2, const float4& az, float B, float B2, float ct1,
+                    float half_ct0, const uint16_t* dm) -> Lane32 {
+    const float* q = s_rel + 3 * (warp * kCullWarpPoints + j * 32 + lane);
+    const float x = q[0], y = q[1], z = q[2];
+    const float I0 = fmaf(a0.x, x, fmaf(a0.y, y, fmaf(a0.z, z, a0.w)));
+    const float I1 = fmaf(a2.x, x, fmaf(a2.y, y, fmaf(a2.z, z, a2.w)));
+    const float Z = fmaf(az.x, x, fmaf(az.y, y, fmaf(az.z, z, az.w)));
+    const float Q1 = fmaf(fdw, Z, -I0), Q3 = fmaf(fdh, Z, -I1);
+    const float m = fminf(fminf(I0, Q1), fminf(I1, Q3));  // NaN only for empty / non-finite slots: never visible
+    const bool cin = m >= B2;                               // certainly inside the image, in front of the camera
+    const float rz = rcp_approx(Z);
+    const float tx = I0 * rz, ty = I1 * rz;
+    const float ix = rintf(tx), iy = rintf(ty);
+    const float e = fmaxf(fabsf(tx - ix), fabsf(ty - iy));
+    const bool pc = e <= fmaf(-ct1, rz, half_ct0);          // the reference rounds to the same depth pixel
+    const float di = fmaf(fminf(iy, fdh1), fdw, fminf(ix, fdw1));
+    Lane32 r;
+    r.go = (MODE == 0) && cin && pc;
+    r.unc = (MODE == 0) ? ((cin && !pc) || (!cin && m >= -B)) : (m >= -B);  // z-buffer splats always go exact
+    r.zf = Z;
+    r.raw = 0u;
+    if (r.go) r.raw = ldg_u16_nc(dm + (int)di);
+    return r;
+  };
+  auto cmp32 = [&](const Lane32& r, float Bz, bool& vis, bool& unc) {
+    const float d = (float)r.raw * (float)p.g.depth_scale;
+    const float mz = fmaf(3.6e-7f, d, Bz);  // 6u d + B_Z: d^ is within 2.1u d of raw*0.001, plus the rounding of d -/+ mz
+    vis = r.go && (r.zf < d - mz);
+    unc = r.go && !vis && !(r.zf >= d + mz);
+  };
 
   for (int fi = 0; fi < nf; ++fi) {
     const CullFrameConsts& c = s_c[fi];
@@ -301,7 +362,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
     const float v = fmaf(a.x, bcx, fmaf(a.y, bcy, fmaf(a.z, bcz, a.w)));
     const float r = __fmaf_ru(fabsf(a.x), bhx, __fmaf_ru(fabsf(a.y), bhy, __fmul_ru(fabsf(a.z), bhz)));
     const uint32_t gb = __ballot_sync(0xffffffffu, __fadd_ru(v, r) >= -B);
-    const uint32_t gm = gb & (gb >> 8) & (gb >> 16) & (gb >> 24) & 0xffu;
+    uint32_t gm = gb & (gb >> 8) & (gb >> 16) & (gb >> 24) & 0xffu;
 
     if (gm != 0u) {
       const float4 a0 = *reinterpret_cast<const float4*>(c.box[0]);
@@ -309,80 +370,43 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
       const float4 az = *reinterpret_cast<const float4*>(c.fz);
       const float B2 = B + B, ct1 = c.ct1, half_ct0 = 0.5f - c.ct0, Bz = c.Bz;
       const uint16_t* dm = p.depth + f * p.depth_stride;
-      // two halves of four groups keep the number of gathers in flight per lane (and registers) bounded
-#pragma unroll
-      for (int h = 0; h < kCullPtsPerLane; h += 4) {
-      uint32_t raw[4];
-      float zf[4];
-      // ---- B: float32 projection of the candidate groups; depth gathers issued for the certain lanes
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = h + jj;
-        raw[jj] = kNoCand;
-        zf[jj] = 0.f;
-        if (gm & (1u << j)) {  // warp-uniform
-          const float I0 = fmaf(a0.x, px[j], fmaf(a0.y, py[j], fmaf(a0.z, pz[j], a0.w)));
-          const float I1 = fmaf(a2.x, px[j], fmaf(a2.y, py[j], fmaf(a2.z, pz[j], a2.w)));
-          const float Z = fmaf(az.x, px[j], fmaf(az.y, py[j], fmaf(az.z, pz[j], az.w)));
-          const float Q1 = fmaf(fdw, Z, -I0), Q3 = fmaf(fdh, Z, -I1);
-          const float m = fminf(fminf(I0, Q1), fminf(I1, Q3));  // NaN inputs propagate a NaN only if all are NaN...
-          const bool bad = !(I0 == I0) | !(I1 == I1) | !(Z == Z);  // ...so test NaN explicitly
-          bool unc = false;
-          if (!bad) {
-            if (m >= B2) {  // certainly inside the image and in front of the camera
-              const float rz = rcp_approx(Z);
-              const float tx = I0 * rz, ty = I1 * rz;
-              const float ix = rintf(tx), iy = rintf(ty);
-              const float e = fmaxf(fabsf(tx - ix), fabsf(ty - iy));
-              if (e <= fmaf(-ct1, rz, half_ct0)) {  // the reference rounds to the same depth pixel
-                const float di = fmaf(fminf(iy, fdh1), fdw, fminf(ix, fdw1));
-                if (MODE == 0) {
-                  raw[jj] = ldg_u16_nc(dm + (int)di);
-                  zf[jj] = Z;
-                } else {
-                  // z-buffer value is float32(z_ref): only certain if the float64 z rounds like this float32 Z — it
-                  // does not in general, so the splat always takes the exact path (still culled/skipped above)
-                  unc = true;
-                }
-              } else {
-                unc = true;
-              }
-            } else if (!(m < -B)) {
-              unc = true;  // inside the guard band of a frustum plane
-            }
-          }
-          const uint32_t bu = __ballot_sync(0xffffffffu, unc);
-          if (bu != 0u) {  // rare, warp-uniform
-            if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
-            nq += __popc(bu);
-          }
+      if (p.stats != nullptr) st_f32 += __popc(gm);
+      // ---- B + C: candidate groups two at a time (two independent dependency chains per lane), then a leftover
+      while (gm & (gm - 1u)) {
+        const int j0 = __ffs(gm) - 1;
+        gm &= gm - 1u;
+        const int j1 = __ffs(gm) - 1;
+        gm &= gm - 1u;
+        const Lane32 r0 = eval32(j0, a0, a2, az, B, B2, ct1, half_ct0, dm);
+        const Lane32 r1 = eval32(j1, a0, a2, az, B, B2, ct1, half_ct0, dm);
+        bool v0, u0, v1, u1;
+        cmp32(r0, Bz, v0, u0);
+        cmp32(r1, Bz, v1, u1);
+        const uint32_t bv0 = __ballot_sync(0xffffffffu, v0), bv1 = __ballot_sync(0xffffffffu, v1);
+        if (lane == j0) myword = bv0;
+        if (lane == j1) myword = bv1;
+        const uint32_t bu0 = __ballot_sync(0xffffffffu, r0.unc | u0), bu1 = __ballot_sync(0xffffffffu, r1.unc | u1);
+        if ((bu0 | bu1) != 0u) {  // rare, warp-uniform
+          if (r0.unc | u0) s_q[warp][nq + __popc(bu0 & lt)] = (uint8_t)((j0 << 5) | lane);
+          nq += __popc(bu0);
+          if (r1.unc | u1) s_q[warp][nq + __popc(bu1 & lt)] = (uint8_t)((j1 << 5) | lane);
+          nq += __popc(bu1);
         }
       }
-      // ---- C: depth comparison in float32 with bounds
-      if (MODE == 0) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = h + jj;
-          if (gm & (1u << j)) {
-            bool vis = false, unc = false;
-            if (raw[jj] != kNoCand) {
-              const float d = (float)raw[jj] * (float)p.g.depth_scale;
-              const float mz = fmaf(3.6e-7f, d, Bz);  // 6u d + B_Z: d^ is within 2.1u d of raw*0.001, plus the rounding of d -/+ mz
-              vis = zf[jj] < d - mz;
-              unc = !vis && !(zf[jj] >= d + mz);
-            }
-            const uint32_t bv = __ballot_sync(0xffffffffu, vis);
-            const uint32_t bu = __ballot_sync(0xffffffffu, unc);
-            if (lane == j) myword = bv;
-            if (bu != 0u) {
-              if (unc) s_q[warp][nq + __popc(bu & lt)] = (uint8_t)((j << 5) | lane);
-              nq += __popc(bu);
-            }
-          }
+      if (gm != 0u) {
+        const int j0 = __ffs(gm) - 1;
+        const Lane32 r0 = eval32(j0, a0, a2, az, B, B2, ct1, half_ct0, dm);
+        bool v0, u0;
+        cmp32(r0, Bz, v0, u0);
+        const uint32_t bv0 = __ballot_sync(0xffffffffu, v0);
+        if (lane == j0) myword = bv0;
+        const uint32_t bu0 = __ballot_sync(0xffffffffu, r0.unc | u0);
+        if (bu0 != 0u) {
+          if (r0.unc | u0) s_q[warp][nq + __popc(bu0 & lt)] = (uint8_t)((j0 << 5) | lane);
+          nq += __popc(bu0);
         }
       }
-      }  // halves
-      if (p.stats != nullptr) st_f32 += __popc(gm) , st_exact += (lane == 0) ? nq : 0;
+      if (p.stats != nullptr) st_exact += (lane == 0) ? nq : 0;
     }
 
     // ---- D: exact float64 reference-order evaluation of the queued lanes (rare)
@@ -396,10 +420,10 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
           const uint32_t code = s_q[warp][t];
           const int j = code >> 5, sl = code & 31;
           const int idx = warp * kCullWarpPoints + j * 32 + sl;
-          double x, y, z;
-          PtTraits<DT>::load(s_pts, idx, x, y, z);
+          double x = 0.0, y = 0.0, z = 0.0;
+          if (idx < cnt) PtTraits<DT>::load(p.pts, base + idx, x, y, z);
           const Proj pr = fstd ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
-          if (in_image(pr, p.g) && pr.z > 0.0) {
+          if (idx < cnt && in_image(pr, p.g) && pr.z > 0.0) {
             const int di = depth_index(pr, p.g);
             if (MODE == 0) {
               if (depth_test(pr.z, ldg_u16_nc(p.depth + f * p.depth_stride + di), p.g)) atomicOr(&s_words[warp][j], 1u << sl);
@@ -423,7 +447,8 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
       if (COUNT) {
         // lanes 0..7 hold the final words; uniform groups: one shared-memory add per non-empty word
         const bool mine_uni = (lane < kCullPtsPerLane) && ((uni_mask >> lane) & 1u);
-        if (mine_uni && myword != 0u && gid != 0u) atomicAdd(&s_cnt[fi * (kCullMaxObjects + 1) + gid], (uint32_t)__popc(myword));
+        if (mine_uni && myword != 0u && gid != 0u)
+          atomicAdd(&s_cnt[fi * kCntWords + (gid >> 1)], (uint32_t)__popc(myword) << ((gid & 1u) * 16u));
         uint32_t mixed = __ballot_sync(0xffffffffu, (lane < kCullPtsPerLane) && !mine_uni && myword != 0u);
         while (mixed) {  // groups that straddle an object boundary (rare): aggregate by id within the warp
           const int j = __ffs(mixed) - 1;
@@ -435,7 +460,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
           const uint32_t am = __ballot_sync(0xffffffffu, act);
           if (act) {
             const uint32_t grp = __match_any_sync(am, id);
-            if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * (kCullMaxObjects + 1) + id], (uint32_t)__popc(grp));
+            if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kCntWords + (id >> 1)], (uint32_t)__popc(grp) << ((id & 1u) * 16u));
           }
         }
       }
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_frame_cull(const CullParams
     __syncthreads();
     for (int i = tid; i < nf * p.n_objects; i += kCullThreads) {
       const int fr = i / p.n_objects, o = i - fr * p.n_objects;
-      const uint32_t v = s_cnt[fr * (kCullMaxObjects + 1) + o + 1];
+      const uint32_t v = (s_cnt[fr * kCntWords + ((o + 1) >> 1)] >> (((o + 1) & 1) * 16)) & 0xffffu;
       if (v != 0u) atomicAdd(p.counts + (int64_t)(f0 + fr) * p.n_objects + o, v);
     }
   }
