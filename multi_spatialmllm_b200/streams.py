@@ -1,0 +1,214 @@
+"""Batch sample writers for the MultiSPA streams, on top of the device records.
+
+The reference builds every sample with per-sample handler calls (two JPEG decodes, one PNG decode and one
+``np.load`` of the whole scene per point, IH:284-305).  Here the host only samples ids; all geometry of a batch
+is one or two kernel launches (msp_annotate_points / msp_pair_annotate) and the host formats the returned
+integers into the reference's JSONL schemas:
+
+  depth_estimation_{coor,dot}  DE-coor:242-251 / DE-dot:253-262   id, image, conversations, height_list, width_list,
+                                                                   question_type, gt_value (mm), ori_coordinates
+  depth_comparison_{coor,dot}  DC-coor:333-343                     + points_info[{x,y,depth,coords,letter}], is_closer_question
+  visual_correspondence_coor_2_coor  VC-coor:382-393               p1_list, p2_list, gt_value
+  camera_movement (9 question types)  CME:205-243                  answer_values{15 keys}, gt_value
+
+Integer semantics are the reference's (round-half-even per-mille / mm, truncating ``int()`` pixel and mm values,
+``<=`` for "closer"), verified against the reference engines' own outputs in tests/test_streams.py.  The text
+templates are NOT shipped here (the reference is CC BY-NC): ``Templates.from_reference(root)`` loads them from a
+user-supplied checkout; the built-in fall-back is a single neutral phrasing per stream.  Random choices use a
+``numpy.random.Generator`` — the streams are statistically like the reference's, not RNG-identical; for
+RNG-identical output run the reference's engine scripts with the drop-in handler.
+"""
+from __future__ import annotations
+
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+
+from .engine import DeviceScene
+
+CAMERA_QUESTION_TYPES = ("x_movement", "y_movement", "z_movement", "yaw_movement", "pitch_movement",
+                         "total_distance", "yaw_angle", "pitch_angle", "displacement_vector")
+
+
+class Templates:
+    """question / answer / task-description phrasings per stream."""
+
+    NEUTRAL = {
+        "depth_estimation": {"task": ["<image>\nPoint coordinates [ x , y ] are per-mille of the image width and height."],
+                             "questions": ["What is the depth in mm of the point [ {x1} , {y1} ]?"],
+                             "answers": ["`{depth}`"]},
+        "depth_comparison": {"task": ["<image>\nPoint coordinates [ x , y ] are per-mille of the image width and height."],
+                             "closer_questions": ["Which of [ {x1} , {y1} ] and [ {x2} , {y2} ] is closer to the camera?"],
+                             "farther_questions": ["Which of [ {x1} , {y1} ] and [ {x2} , {y2} ] is farther from the camera?"],
+                             "closer_answers": ["[ {correct_x} , {correct_y} ]"], "farther_answers": ["[ {correct_x} , {correct_y} ]"]},
+        "visual_correspondence": {"task": ["Image-1: <image>\nImage-2: <image>\nCoordinates [ x , y ] are per-mille of width and height."],
+                                  "questions": ["Where is the point [ {x1} , {y1} ] of Image-1 in Image-2?"],
+                                  "answers": ["[ {x2} , {y2} ]"]},
+        "camera_movement": {"task": ["Image-1: <image>\nImage-2: <image>\nDescribe the camera motion from Image-1 to Image-2."],
+                            "questions": {q: [f"Report {q} of the second camera relative to the first."] for q in CAMERA_QUESTION_TYPES},
+                            "answers": {q: ["`{" + q + "}`"] for q in CAMERA_QUESTION_TYPES}},
+    }
+
+    def __init__(self, tables=None):
+        self.t = tables or self.NEUTRAL
+
+    @classmethod
+    def from_reference(cls, reference_root: str) -> "Templates":
+        """Import the phrasings from a reference checkout (they stay in the user's copy; nothing is vendored)."""
+        def load(rel, name):
+            path = os.path.join(reference_root, rel)
+            spec = importlib.util.spec_from_file_location(name, path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod
+        cm = load("spatial_engine/camera_movement/TEMPLATES.py", "_msp_ref_cm_templates")
+        t = dict(cls.NEUTRAL)
+        t["camera_movement"] = {"task": cm.TASK_DESCRIPTION, "questions": cm.QUESTION_TEMPLATES, "answers": cm.ANSWER_TEMPLATES}
+        return cls(t)
+
+
+def _pick(rng, seq):
+    return seq[int(rng.integers(0, len(seq)))]
+
+
+def _conversation(task, question, answer):
+    return [{"from": "human", "value": f"{task}\n{question}"}, {"from": "gpt", "value": answer}]
+
+
+# ------------------------------------------------------------------------------------------------
+# depth perception
+# ------------------------------------------------------------------------------------------------
+def annotate(sc: DeviceScene, frames, points):
+    a = sc.annotate_points(np.asarray(points, np.int32), np.asarray(frames, np.int32))
+    return {k: v.cpu().numpy() for k, v in a.items()}
+
+
+def depth_estimation_samples(sc, scene_id, image_ids, frames, points, variant="coor", templates=None, rng=None):
+    """One sample per (frame, point); invisible points are skipped like DE-coor:207-213."""
+    tp, rng = (templates or Templates()).t["depth_estimation"], rng or np.random.default_rng(0)
+    H, W = sc.image_hw
+    a = annotate(sc, frames, points)
+    out = []
+    for i, (f, p) in enumerate(zip(frames, points)):
+        if not a["visible"][i]:
+            continue
+        x, y = (int(v) for v in a["permille"][i])
+        depth, (u, v) = int(a["depth_mm"][i]), (int(c) for c in a["pix"][i])
+        image_id = image_ids[f]
+        q = _pick(rng, tp["questions"]).format(x1=x, y1=y)
+        ans = _pick(rng, tp["answers"]).format(x1=x, y1=y, depth=depth)
+        img = f"{scene_id}/{image_id}.jpg" if variant == "coor" else f"{scene_id}/{image_id}_p{int(p)}_annotated.jpg"
+        out.append({"id": f"{scene_id}_{image_id}_point{int(p)}", "image": [img],
+                    "conversations": _conversation(_pick(rng, tp["task"]), q, ans),
+                    "height_list": [H], "width_list": [W], "question_type": f"depth_estimation_{variant}",
+                    "gt_value": depth, "ori_coordinates": [u, v]})
+    return out
+
+
+def depth_comparison_samples(sc, scene_id, image_ids, frames, point_pairs, closer_question, variant="coor", templates=None, rng=None):
+    """One sample per (frame, (pA, pB)); equal mm depths are rejected (DC-coor:289-294), "closer" uses <= (DC-coor:304)."""
+    tp, rng = (templates or Templates()).t["depth_comparison"], rng or np.random.default_rng(0)
+    H, W = sc.image_hw
+    pp = np.asarray(point_pairs, np.int32).reshape(-1, 2)
+    fr2 = np.repeat(np.asarray(frames, np.int32), 2)
+    a = annotate(sc, fr2, pp.reshape(-1))
+    out = []
+    for i, f in enumerate(frames):
+        info = []
+        for s in range(2):
+            k = 2 * i + s
+            if a["visible"][k]:
+                info.append({"x": int(a["permille"][k][0]), "y": int(a["permille"][k][1]), "depth": int(a["depth_mm"][k]),
+                             "coords": (int(a["pix"][k][0]), int(a["pix"][k][1])), "letter": "AB"[s]})
+        if len(info) != 2 or info[0]["depth"] == info[1]["depth"]:
+            continue
+        p1, p2 = info
+        closer, farther = (p1, p2) if p1["depth"] <= p2["depth"] else (p2, p1)
+        is_closer = bool(closer_question[i])
+        pick = closer if is_closer else farther
+        kind = "closer" if is_closer else "farther"
+        q = _pick(rng, tp[f"{kind}_questions"]).format(x1=p1["x"], y1=p1["y"], x2=p2["x"], y2=p2["y"])
+        ans = _pick(rng, tp[f"{kind}_answers"]).format(correct_x=pick["x"], correct_y=pick["y"])
+        image_id = image_ids[f]
+        out.append({"id": f"{scene_id}_{image_id}_p{int(pp[i][0])}_p{int(pp[i][1])}", "image": [f"{scene_id}/{image_id}.jpg"],
+                    "conversations": _conversation(_pick(rng, tp["task"]), q, ans), "height_list": [H], "width_list": [W],
+                    "question_type": "depth_comparison_coordinate" if variant == "coor" else "depth_comparison_dot",
+                    "gt_value": [pick["x"], pick["y"]], "points_info": info, "is_closer_question": is_closer})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# pair streams
+# ------------------------------------------------------------------------------------------------
+def visual_correspondence_samples(sc, scene_id, image_ids, pairs, sel, sel_mode=1, start_idx=0, templates=None, rng=None):
+    """One sample per ordered pair (image1, image2); ``sel`` picks the common visible point (VC-coor:303-315)."""
+    tp, rng = (templates or Templates()).t["visual_correspondence"], rng or np.random.default_rng(0)
+    H, W = sc.image_hw
+    rec = sc.records_to_numpy(sc.pair_annotate(np.asarray(pairs, np.int32), sel, sel_mode))
+    out = []
+    for i, ((a, b), r) in enumerate(zip(np.asarray(pairs).tolist(), rec)):
+        if r["point_id"] < 0 or r["flags"] != 3:          # no common point / failed re-check (VC-coor:304-337)
+            continue
+        x1, y1, x2, y2 = (int(v) for v in r["permille"])
+        i1, i2 = image_ids[a], image_ids[b]
+        q = _pick(rng, tp["questions"]).format(x1=x1, y1=y1, x2=x2, y2=y2)
+        ans = _pick(rng, tp["answers"]).format(x1=x1, y1=y1, x2=x2, y2=y2)
+        out.append({"id": f"{scene_id}_{i1}_{i2}_{start_idx + i}", "image": [f"{scene_id}/{i1}.jpg", f"{scene_id}/{i2}.jpg"],
+                    "conversations": _conversation(_pick(rng, tp["task"]), q, ans), "height_list": [H, H], "width_list": [W, W],
+                    "question_type": "visual_correspondence_coor_2_coor", "p1_list": [(x1, y1)], "p2_list": [(x2, y2)],
+                    "gt_value": [x2, y2]})
+    return out
+
+
+def camera_answer_values(rel_disp, yaw_angle, pitch_angle):
+    """CME:168-172 (yaw wrap) and CME:205-225 (signs, truncating ints) from the device record of the ORDERED pair."""
+    if abs(yaw_angle) > 180:
+        yaw_angle = yaw_angle - 360 if yaw_angle > 0 else yaw_angle + 360
+    d = np.asarray(rel_disp, dtype=np.float64)
+    return {
+        "x_movement": "right" if d[0] > 0 else "left", "y_movement": "down" if d[1] > 0 else "up",
+        "z_movement": "forward" if d[2] > 0 else "backward",
+        "yaw_movement": "left" if yaw_angle > 0 else "right", "pitch_movement": "up" if pitch_angle > 0 else "down",
+        "x_distance": int(abs(d[0]) * 1000), "y_distance": int(abs(d[1]) * 1000), "z_distance": int(abs(d[2]) * 1000),
+        "yaw_angle": int(abs(yaw_angle)), "pitch_angle": int(abs(pitch_angle)),
+        "x_value": int(d[0] * 1000), "y_value": int(d[1] * 1000), "z_value": int(d[2] * 1000),
+        "total_distance": int(np.linalg.norm(d) * 1000), "displacement_vector": d.tolist(),
+    }
+
+
+def camera_movement_samples(sc, scene_id, image_ids, pairs, question_type, start_idx=0, templates=None, rng=None):
+    """One sample per ORDERED pair (image1 -> image2); swap a pair by passing it reversed (CME:163-167)."""
+    assert question_type in CAMERA_QUESTION_TYPES
+    tp, rng = (templates or Templates()).t["camera_movement"], rng or np.random.default_rng(0)
+    H, W = sc.image_hw
+    pairs = np.asarray(pairs, np.int32).reshape(-1, 2)
+    rec = sc.records_to_numpy(sc.pair_annotate(pairs, np.zeros(len(pairs), np.uint32), 0))
+    out = []
+    for i, ((a, b), r) in enumerate(zip(pairs.tolist(), rec)):
+        if not (r["overlap"] >= 0.1):                     # CME:199-201: low / undefined overlap is not supported
+            continue
+        av = camera_answer_values(r["rel_disp"], float(r["dyaw"]), float(r["dpitch"]))
+        q = _pick(rng, tp["questions"][question_type])
+        ans = _pick(rng, tp["answers"][question_type]).format(**av)
+        out.append({"id": start_idx + i, "image": [f"{scene_id}/{image_ids[a]}.jpg", f"{scene_id}/{image_ids[b]}.jpg"],
+                    "conversations": _conversation(_pick(rng, tp["task"]), q, ans), "height_list": [H, H], "width_list": [W, W],
+                    "answer_values": av, "question_type": question_type, "gt_value": av[question_type]})
+    return out
+
+
+def to_eval_sample(sample: dict) -> dict:
+    """DE-coor / VC-coor / CME convert_train_sample_to_eval_sample: the first human turn becomes ``text``."""
+    s = dict(sample)
+    s["text"] = s.pop("conversations")[0]["value"]
+    return s
+
+
+def write_jsonl(samples, path: str) -> int:
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    with open(path, "w") as f:
+        for s in samples:
+            f.write(json.dumps(s) + "\n")
+    return len(samples)

@@ -1,0 +1,134 @@
+"""Engine-level goldens: run the reference's own QA engines (numeric core only) on the scannet_small fixture.
+
+    python tests/golden/make_golden_engines.py        (build container only; needs /root/reference)
+
+Writes tests/golden/engines_small.json with the NUMERIC fields of the samples the unmodified reference engines
+produce (no template text is stored):
+  depth_estimation_coor   DepthEstimationCoorQAEngine.generate_qa_training_single_scene   (DE-coor:175-254)
+  depth_comparison_coor   DepthComparisonCoorQAEngine.generate_qa_training_single_scene   (DC-coor:240-346)
+  visual_correspondence   build_training_sample                                            (VC-coor:264-394)
+  camera_movement         build_training_sample for three question types                   (CME:153-245)
+One shim is needed beyond mmengine: the reference's visual-correspondence engine calls
+SceneInfoHandler.get_image_size, which the reference handler does not define; it is aliased to
+get_image_shape on the instance.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import pickle
+import random
+import sys
+import tempfile
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from multi_spatialmllm_b200 import synth  # noqa: E402
+from oracle import ref_layout, ref_shim  # noqa: E402
+
+
+def main():
+    ref = ref_shim.import_reference()
+    g = dict(np.load(os.path.join(HERE, "scannet_small.npz")))
+    s = synth.SynthScene("scene0011_00", g["points"], g["instance_ids"], int(g["num_objects"]), g["axis_align"], g["c2w"],
+                         g["K"], tuple(int(v) for v in g["image_hw"]), tuple(int(v) for v in g["depth_hw"]),
+                         depth=g["depth"], image_ids=[str(v) for v in g["image_ids"]])
+    out = {}
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    with tempfile.TemporaryDirectory() as tmp, np.errstate(all="ignore"):
+        info_path = ref_layout.write_split([s], tmp)
+        with quiet:
+            h = ref.info_handler.SceneInfoHandler(info_path, posed_images_root=os.path.join(tmp, "posed_images"),
+                                                  instance_data_root=os.path.join(tmp, "scannet_instance_data"))
+            _, vis = ref.mvi.process_scene(s.scene_id, h, os.path.join(tmp, "w.txt"))
+            _, rel = ref.cfr.process_scene(s.scene_id, h, os.path.join(tmp, "w.txt"))
+        pkl = os.path.join(tmp, "vis.pkl")
+        with open(pkl, "wb") as f:
+            pickle.dump({s.scene_id: vis}, f)
+        with quiet:
+            ref.mvi.convert_pkl_to_parquet(pkl)
+            vih = ref.info_handler.VisibilityInfoHandler(pkl.replace(".pkl", ".parquet"))
+            from spatial_engine.depth_perception import depth_estimation_coor_engine as de
+            from spatial_engine.depth_perception import depth_comparison_coor_engine as dc
+            from spatial_engine.visual_correspondence import visual_correspondence_qa_engine_coor_2_coor as vc
+            # the camera-movement engine does `from TEMPLATES import ...` (it is run from its own directory)
+            sys.path.insert(0, os.path.join(ref_shim.REFERENCE_ROOT, "spatial_engine", "camera_movement"))
+            from spatial_engine.camera_movement import camera_movement_engine_train_val as cme
+
+        # ---- depth estimation (coor)
+        eng = de.DepthEstimationCoorQAEngine.__new__(de.DepthEstimationCoorQAEngine)
+        eng.scene_info, eng.visibility_info = h, vih
+        eng.max_samples, eng.max_n_points_per_image, eng.warning_file = -1, 3, os.path.join(tmp, "w.txt")
+        eng.templates = {"questions": ["{x1} {y1}"], "answers": ["{x1} {y1} {depth}"]}
+        eng.task_description = ["t"]
+        random.seed(4)
+        with quiet:
+            samples = eng.generate_qa_training_single_scene(s.scene_id)
+        out["depth_estimation_coor"] = [
+            {"image_id": x["image"][0].split("/")[1][:5], "point": int(x["id"].split("point")[1]),
+             "xy_permille": [int(v) for v in x["conversations"][0]["value"].split("\n")[1].split()],
+             "gt_value": int(x["gt_value"]), "ori_coordinates": [int(v) for v in x["ori_coordinates"]]} for x in samples]
+
+        # ---- depth comparison (coor)
+        eng2 = dc.DepthComparisonCoorQAEngine.__new__(dc.DepthComparisonCoorQAEngine)
+        eng2.scene_info, eng2.visibility_info = h, vih
+        eng2.max_samples, eng2.max_n_points_per_image, eng2.warning_file = -1, 2, os.path.join(tmp, "w.txt")
+        one = ["{x1} {y1} {x2} {y2}"]
+        eng2.templates = {"closer_questions": one, "farther_questions": one, "closer_answers": ["{correct_x} {correct_y}"],
+                          "farther_answers": ["{correct_x} {correct_y}"]}
+        eng2.task_description = ["t"]
+        random.seed(6)
+        with quiet:
+            samples = eng2.generate_qa_training_single_scene(s.scene_id)
+        out["depth_comparison_coor"] = [
+            {"image_id": x["image"][0].split("/")[1][:5], "points": [int(t[1:]) for t in x["id"].split("_")[-2:]],
+             "gt_value": [int(v) for v in x["gt_value"]], "is_closer_question": bool(x["is_closer_question"]),
+             "points_info": [{"x": int(q["x"]), "y": int(q["y"]), "depth": int(q["depth"]), "coords": [int(c) for c in q["coords"]],
+                              "letter": q["letter"]} for q in x["points_info"]]} for x in samples]
+
+        # ---- visual correspondence (coor_2_coor)
+        h.get_image_size = h.get_image_shape            # reference defect, SURVEY.md §2.3
+        rows = [{"scene_id": s.scene_id, "image_id1": a, "image_id2": b, **v} for (a, b), v in rel.items() if v["overlap"] > 0]
+        vis_dict = {s.scene_id: vis}
+        vc.TASK_DESCRIPTION, vc.TEMPLATES = ["t"], {"questions": ["q"], "answers": ["a"]}
+        random.seed(1)
+        res = []
+        for i, row in enumerate(rows):
+            with quiet:
+                smp = vc.build_training_sample(h, row, i, vis_dict, os.path.join(tmp, "w.txt"), max_points_per_pair=1)
+            if smp is None:
+                continue
+            res.append({"images": [p.split("/")[1][:5] for p in smp["image"]], "p1": [int(v) for v in smp["p1_list"][0]],
+                        "p2": [int(v) for v in smp["p2_list"][0]], "gt_value": [int(v) for v in smp["gt_value"]]})
+        out["visual_correspondence_coor_2_coor"] = res
+
+        # ---- camera movement
+        cme.TASK_DESCRIPTION = ["t"]
+        for qt in list(cme.QUESTION_TEMPLATES):
+            cme.QUESTION_TEMPLATES[qt], cme.ANSWER_TEMPLATES[qt] = ["q"], ["a"]
+        random.seed(0)
+        res = []
+        for i, row in enumerate(rows):
+            for qt in ("total_distance", "yaw_angle", "displacement_vector"):
+                with quiet:
+                    smp = cme.build_training_sample(h, pd.Series(row), i, qt)
+                av = smp["answer_values"]
+                res.append({"images": [p.split("/")[1][:5] for p in smp["image"]], "question_type": qt,
+                            "row": {k: float(row[k]) for k in ("overlap", "distance", "yaw", "pitch")},
+                            "answer_values": {k: (v if isinstance(v, (str, list)) else int(v)) for k, v in av.items()},
+                            "gt_value": smp["gt_value"] if isinstance(smp["gt_value"], (str, list)) else int(smp["gt_value"])})
+        out["camera_movement"] = res
+    with open(os.path.join(HERE, "engines_small.json"), "w") as f:
+        json.dump(out, f)
+    print({k: len(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

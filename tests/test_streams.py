@@ -1,0 +1,125 @@
+"""Sample writers (multi_spatialmllm_b200/streams.py) against the NUMERIC output of the reference's own engines
+(tests/golden/engines_small.json, produced by tests/golden/make_golden_engines.py from the unmodified reference)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import geometry as og
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def engines_golden():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "engines_small.json")))
+
+
+def test_oracle_camera_values_match_reference_engine(golden_scannet, engines_golden):
+    """CPU: the oracle's restatement of CME:168-225 equals the reference engine's answer_values."""
+    g = golden_scannet
+    valid = [str(v) for v in g["valid_ids"]]
+    for it in engines_golden["camera_movement"]:
+        i1, i2 = (valid.index(x) for x in it["images"])
+        swapped = i1 > i2
+        yaw, pitch = it["row"]["yaw"], it["row"]["pitch"]
+        if swapped:
+            yaw, pitch = -yaw, -pitch
+        av = og.camera_movement_values(g["ref_E_aligned"][i1], g["ref_E_aligned"][i2], yaw, pitch)
+        for k, v in av.items():
+            if k == "displacement_vector":
+                np.testing.assert_allclose(v, it["answer_values"][k], rtol=1e-12, atol=1e-14)
+            else:
+                assert v == it["answer_values"][k], k
+
+
+def test_oracle_point_integers_match_reference_engines(golden_scannet, engines_golden):
+    g = golden_scannet
+    ids = [str(v) for v in g["image_ids"]]
+    valid = [str(v) for v in g["valid_ids"]]
+    pts = g["points"].astype(np.float64)
+    for it in engines_golden["depth_estimation_coor"]:
+        f, k = ids.index(it["image_id"]), valid.index(it["image_id"])
+        a = og.annotate_point(pts[it["point"]], g["K"], g["ref_E_aligned"][k], g["depth"][f], 968, 1296)
+        assert [a["x_permille"], a["y_permille"]] == it["xy_permille"]
+        assert a["depth_mm"] == it["gt_value"] and list(a["pix"]) == it["ori_coordinates"]
+
+
+def _scene(g):
+    from multi_spatialmllm_b200.engine import DeviceScene
+    return DeviceScene(g["points"], g["K"], g["c2w"], axis_align=g["axis_align"], depth=g["depth"],
+                       instance_ids=g["instance_ids"], num_objects=int(g["num_objects"]))
+
+
+@pytest.mark.gpu
+def test_depth_streams_match_reference_engines(golden_scannet, engines_golden):
+    from multi_spatialmllm_b200 import streams
+    g = golden_scannet
+    ids = [str(v) for v in g["image_ids"]]
+    sc = _scene(g)
+    de = engines_golden["depth_estimation_coor"]
+    out = streams.depth_estimation_samples(sc, "scene0011_00", ids, [ids.index(x["image_id"]) for x in de], [x["point"] for x in de])
+    assert len(out) == len(de)
+    for s, it in zip(out, de):
+        assert s["id"] == f"scene0011_00_{it['image_id']}_point{it['point']}" and s["image"] == [f"scene0011_00/{it['image_id']}.jpg"]
+        assert s["gt_value"] == it["gt_value"] and s["ori_coordinates"] == it["ori_coordinates"]
+        assert s["height_list"] == [968] and s["width_list"] == [1296] and s["question_type"] == "depth_estimation_coor"
+        assert str(it["xy_permille"][0]) in s["conversations"][0]["value"] and str(it["gt_value"]) in s["conversations"][1]["value"]
+    dc = engines_golden["depth_comparison_coor"]
+    # feed the points in the order the reference stored them (after its own shuffle): points_info order
+    pairs = []
+    for it in dc:
+        by_xy = {(q["x"], q["y"]): q for q in it["points_info"]}
+        a = streams.annotate(sc, [ids.index(it["image_id"])] * 2, it["points"])
+        order = [tuple(int(v) for v in a["permille"][k]) for k in range(2)]
+        first = it["points"][0] if order[0] == (it["points_info"][0]["x"], it["points_info"][0]["y"]) else it["points"][1]
+        second = it["points"][1] if first == it["points"][0] else it["points"][0]
+        pairs.append((first, second))
+        assert set(order) == set(by_xy)
+    out = streams.depth_comparison_samples(sc, "scene0011_00", ids, [ids.index(x["image_id"]) for x in dc], pairs,
+                                           [x["is_closer_question"] for x in dc])
+    assert len(out) == len(dc)
+    for s, it in zip(out, dc):
+        assert s["gt_value"] == it["gt_value"] and s["is_closer_question"] == it["is_closer_question"]
+        for q, r in zip(s["points_info"], it["points_info"]):
+            assert (q["x"], q["y"], q["depth"], list(q["coords"])) == (r["x"], r["y"], r["depth"], r["coords"])
+
+
+@pytest.mark.gpu
+def test_pair_streams_match_reference_engines(golden_scannet, engines_golden, tmp_path):
+    from multi_spatialmllm_b200 import streams
+    g = golden_scannet
+    ids = [str(v) for v in g["image_ids"]]
+    sc = _scene(g)
+    sc.project_visibility()
+    mb = sc.mask_bool()
+    # visual correspondence: the reference's (p1, p2) must be produced by SOME common point k of that ordered pair
+    for it in engines_golden["visual_correspondence_coor_2_coor"]:
+        a, b = (ids.index(x) for x in it["images"])
+        n_common = int((mb[a] & mb[b]).sum())
+        pairs = np.tile(np.array([[a, b]], np.int32), (n_common, 1))
+        out = streams.visual_correspondence_samples(sc, "scene0011_00", ids, pairs, np.arange(n_common, dtype=np.uint32), sel_mode=0)
+        assert len(out) == n_common
+        got = {(tuple(s["p1_list"][0]), tuple(s["p2_list"][0])) for s in out}
+        assert (tuple(it["p1"]), tuple(it["p2"])) in got
+        assert out[0]["image"] == [f"scene0011_00/{it['images'][0]}.jpg", f"scene0011_00/{it['images'][1]}.jpg"]
+        assert out[0]["gt_value"] == list(out[0]["p2_list"][0])
+    # camera movement: every field of answer_values
+    cm = engines_golden["camera_movement"]
+    for qt in ("total_distance", "yaw_angle", "displacement_vector"):
+        items = [it for it in cm if it["question_type"] == qt]
+        pairs = np.array([[ids.index(x) for x in it["images"]] for it in items], np.int32)
+        out = streams.camera_movement_samples(sc, "scene0011_00", ids, pairs, qt)
+        assert len(out) == len(items)
+        for s, it in zip(out, items):
+            for k, v in it["answer_values"].items():
+                if k == "displacement_vector":
+                    np.testing.assert_allclose(s["answer_values"][k], v, rtol=1e-11, atol=1e-13)
+                else:
+                    assert s["answer_values"][k] == v, (k, it["images"])
+            if qt != "displacement_vector":
+                assert s["gt_value"] == it["gt_value"]
+    n = streams.write_jsonl([streams.to_eval_sample(s) for s in out], str(tmp_path / "cm.jsonl"))
+    rows = [json.loads(l) for l in open(tmp_path / "cm.jsonl")]
+    assert n == len(rows) and "text" in rows[0] and "conversations" not in rows[0]
