@@ -256,3 +256,39 @@ def process_scene_relations(scene: DeviceScene, image_ids):
             "yaw": float(r["dyaw"]), "pitch": float(r["dpitch"]),
         }
     return out
+
+
+class DeviceVideo:
+    """One TAPVid-3D clip resident in HBM (single_object_movement_engine_coord.py:441-451)."""
+
+    def __init__(self, tracks_xyz, w2c, fxfycxcy, image_hw, device="cuda:0"):
+        _require_cuda()
+        self.device = torch.device(device)
+        self.tracks = _to_device(np.asarray(tracks_xyz, dtype=np.float32), torch.float32, self.device)
+        self.T, self.N = int(self.tracks.shape[0]), int(self.tracks.shape[1])
+        self.w2c = _to_device(np.asarray(w2c, dtype=np.float64).reshape(self.T, 16), torch.float64, self.device)
+        self.intr = _to_device(np.asarray(fxfycxcy, dtype=np.float64).reshape(4), torch.float64, self.device)
+        self.image_hw = (int(image_hw[0]), int(image_hw[1]))
+        self.world = self.uvn = self.permille = self.valid = None
+
+    def project(self):
+        """World transform + pinhole projection of every (frame, track) (OM-coord:446-451, 293-315)."""
+        T, N = self.T, self.N
+        self.world = torch.empty((T, N, 3), dtype=torch.float64, device=self.device)
+        self.uvn = torch.empty((T, N, 2), dtype=torch.float64, device=self.device)
+        self.permille = torch.empty((T, N, 2), dtype=torch.int32, device=self.device)
+        self.valid = torch.empty((T, N), dtype=torch.uint8, device=self.device)
+        check(lib.msp_track_project(_ptr(self.tracks), _ptr(self.w2c), _ptr(self.intr), T, N, self.image_hw[0],
+                                    self.image_hw[1], _ptr(self.world), _ptr(self.uvn), _ptr(self.permille),
+                                    _ptr(self.valid), _stream()), "msp_track_project")
+        return self
+
+    def pair_displacement(self, triples):
+        """(M,3) int32 (frame1, frame2, track) -> (M,5) float64: dist, d_cam1 xyz, camera baseline (OM-coord:329-356)."""
+        if self.world is None:
+            self.project()
+        tri = _to_device(np.asarray(triples, dtype=np.int32).reshape(-1, 3), torch.int32, self.device)
+        out = torch.empty((int(tri.shape[0]), 5), dtype=torch.float64, device=self.device)
+        check(lib.msp_track_pair_displacement(_ptr(self.world), _ptr(self.w2c), self.T, self.N, _ptr(tri),
+                                              int(tri.shape[0]), _ptr(out), _stream()), "msp_track_pair_displacement")
+        return out

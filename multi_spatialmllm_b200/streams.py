@@ -27,7 +27,7 @@ import sys
 
 import numpy as np
 
-from .engine import DeviceScene
+from .engine import DeviceScene, DeviceVideo
 
 CAMERA_QUESTION_TYPES = ("x_movement", "y_movement", "z_movement", "yaw_movement", "pitch_movement",
                          "total_distance", "yaw_angle", "pitch_angle", "displacement_vector")
@@ -196,6 +196,43 @@ def camera_movement_samples(sc, scene_id, image_ids, pairs, question_type, start
         out.append({"id": start_idx + i, "image": [f"{scene_id}/{image_ids[a]}.jpg", f"{scene_id}/{image_ids[b]}.jpg"],
                     "conversations": _conversation(_pick(rng, tp["task"]), q, ans), "height_list": [H, H], "width_list": [W, W],
                     "answer_values": av, "question_type": question_type, "gt_value": av[question_type]})
+    return out
+
+
+def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="tapvid3d_total_distance",
+                            object_thr=0.01, camera_thr=0.01, templates=None, rng=None):
+    """TAPVid-3D two-frame samples for (frame1, frame2, track) triples (OM-coord:317-404).
+
+    Static points (||dw|| < object_thr) get distance 0 and a zero vector (OM-coord:337-341); a triple whose point
+    does not project inside either frame is skipped (OM-coord:360-362).
+    """
+    tp = (templates or Templates()).t.get("object_movement", {
+        "task": ["Image-1: <image>\nImage-2: <image>\nCoordinates [ x , y ] are per-mille of width and height."],
+        "questions": ["How far did the point at [ {x1} , {y1} ] in Image-1 move (mm), in camera-1 axes?"],
+        "answers": ["`{total_distance}` [ {x_value} , {y_value} , {z_value} ]"]})
+    rng = rng or np.random.default_rng(0)
+    H, W = vid.image_hw
+    tri = np.asarray(triples, np.int32).reshape(-1, 3)
+    disp = vid.pair_displacement(tri).cpu().numpy()
+    pm, ok = vid.permille.cpu().numpy(), vid.valid.cpu().numpy().astype(bool)
+    out = []
+    for (f1, f2, pt), d in zip(tri.tolist(), disp):
+        if not (ok[f1, pt] and ok[f2, pt]):
+            continue
+        moving = bool(d[0] >= object_thr)
+        dist, dcam = (float(d[0]), d[1:4].copy()) if moving else (0, np.zeros(3))
+        x1, y1 = (int(v) for v in pm[f1, pt])
+        x2, y2 = (int(v) for v in pm[f2, pt])
+        q = _pick(rng, tp["questions"]).format(x1=x1, y1=y1)
+        ans = _pick(rng, tp["answers"]).format(total_distance=round(dist * 1000), x_value=round(float(dcam[0]) * 1000),
+                                               y_value=round(float(dcam[1]) * 1000), z_value=round(float(dcam[2]) * 1000))
+        if not moving:
+            ans = "The point did not move. " + ans
+        out.append({"id": f"{video_id}_{f1}_{f2}_{pt}", "image": [f"{video_id}/{f1:05d}.jpg", f"{video_id}/{f2:05d}.jpg"],
+                    "conversations": _conversation(_pick(rng, tp["task"]), q, ans), "height_list": [H, H], "width_list": [W, W],
+                    "gt_value": int(dist * 1000) if "total_distance" in question_type else dcam.tolist(),
+                    "question_type": question_type, "point_moving": int(moving), "cam_moving": int(d[4] >= camera_thr),
+                    "p1": (x1, y1), "p2": (x2, y2)})
     return out
 
 

@@ -125,6 +125,33 @@ def main():
                             "answer_values": {k: (v if isinstance(v, (str, list)) else int(v)) for k, v in av.items()},
                             "gt_value": smp["gt_value"] if isinstance(smp["gt_value"], (str, list)) else int(smp["gt_value"])})
         out["camera_movement"] = res
+    # ---- object movement (TAPVid-3D): format_training_samples on the tapvid_small fixture (OM-coord:317-404)
+    with quiet:
+        from spatial_engine.object_movement import single_object_movement_engine_coord as om
+    tv = dict(np.load(os.path.join(HERE, "tapvid_small.npz")))
+    T, N, _ = tv["tracks_xyz"].shape
+    H, W = (int(v) for v in tv["image_hw"])
+    eng3 = om.TwoFrameVideoQAEngine.__new__(om.TwoFrameVideoQAEngine)
+    eng3.object_not_moving_threshold, eng3.camera_not_moving_threshold = 0.01, 0.01
+    eng3.task_description, eng3.question_templates = ["t"], ["{x1} {y1}"]
+    eng3.answer_templates = ["{total_distance} {x_value} {y_value} {z_value}"]
+    eng3.question_type = "tapvid3d_total_distance"
+    rng = np.random.default_rng(5)
+    trip = [{"frame1": int(a), "frame2": int(b), "point_index": int(c)}
+            for a, b, c in zip(rng.integers(0, T, 120), rng.integers(0, T, 120), rng.integers(0, N, 120)) if a != b]
+    # float64 camera-frame tracks: the pinned numpy 1.26 promotes float32 + 1e-8 to float64 (see make_golden.py)
+    with quiet:
+        data = eng3.format_training_samples(trip, tv["fxfycxcy"], "video00003", tv["ref_world"].copy(),
+                                            tv["tracks_xyz"].astype(np.float64), H, W, tv["w2c"])
+    res = []
+    for e in data:
+        f1, f2, pt = (int(v) for v in e["id"].split("_")[1:4])
+        nums = [int(v) for v in e["conversations"][1]["value"].replace("The point did not move. ", "").split()]
+        res.append({"frame1": f1, "frame2": f2, "point": pt, "p1": [int(v) for v in e["p1"]], "p2": [int(v) for v in e["p2"]],
+                    "total_distance": nums[0], "xyz": nums[1:], "gt_value": int(e["gt_value"]),
+                    "point_moving": int(e["point_moving"]), "cam_moving": int(e["cam_moving"])})
+    out["object_movement"] = res
+    out["object_movement_requested"] = [[t["frame1"], t["frame2"], t["point_index"]] for t in trip]
     with open(os.path.join(HERE, "engines_small.json"), "w") as f:
         json.dump(out, f)
     print({k: len(v) for k, v in out.items()})

@@ -123,3 +123,33 @@ def test_pair_streams_match_reference_engines(golden_scannet, engines_golden, tm
     n = streams.write_jsonl([streams.to_eval_sample(s) for s in out], str(tmp_path / "cm.jsonl"))
     rows = [json.loads(l) for l in open(tmp_path / "cm.jsonl")]
     assert n == len(rows) and "text" in rows[0] and "conversations" not in rows[0]
+
+
+def test_oracle_track_values_match_reference_engine(golden_tapvid, engines_golden):
+    """CPU: oracle restatement of OM-coord:329-376 against format_training_samples of the reference."""
+    g = golden_tapvid
+    H, W = (int(v) for v in g["image_hw"])
+    for it in engines_golden["object_movement"]:
+        r = og.track_pair_sample_values(g["ref_world"], g["tracks_xyz"], g["w2c"], g["fxfycxcy"], it["frame1"], it["frame2"],
+                                        it["point"], H, W)
+        assert r is not None
+        assert list(r["p1"]) == it["p1"] and list(r["p2"]) == it["p2"]
+        assert r["total_distance_mm"] == it["total_distance"] and list(r["xyz_mm"]) == it["xyz"]
+        assert (r["point_moving"], r["cam_moving"]) == (it["point_moving"], it["cam_moving"])
+
+
+@pytest.mark.gpu
+def test_object_movement_stream_matches_reference_engine(golden_tapvid, engines_golden):
+    from multi_spatialmllm_b200 import streams
+    from multi_spatialmllm_b200.engine import DeviceVideo
+    g = golden_tapvid
+    vid = DeviceVideo(g["tracks_xyz"], g["w2c"], g["fxfycxcy"], g["image_hw"]).project()
+    out = streams.object_movement_samples(vid, "video00003", engines_golden["object_movement_requested"])
+    want = engines_golden["object_movement"]
+    assert [s["id"] for s in out] == [f"video00003_{w['frame1']}_{w['frame2']}_{w['point']}" for w in want]   # same skips
+    for s, w in zip(out, want):
+        assert list(s["p1"]) == w["p1"] and list(s["p2"]) == w["p2"]
+        assert (s["gt_value"], s["point_moving"], s["cam_moving"]) == (w["gt_value"], w["point_moving"], w["cam_moving"])
+        nums = [int(v) for v in s["conversations"][1]["value"].replace("The point did not move. ", "").replace("`", " ")
+                .replace("[", " ").replace("]", " ").replace(",", " ").split()]
+        assert nums == [w["total_distance"]] + w["xyz"]
