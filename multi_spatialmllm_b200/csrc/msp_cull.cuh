@@ -43,6 +43,9 @@ constexpr int kCullMaxObjects = 63;
 #ifndef MSP_CULL_MINBLOCKS
 #define MSP_CULL_MINBLOCKS 4
 #endif
+#ifndef MSP_CULL_PREFETCH
+#define MSP_CULL_PREFETCH 0  // 1: each CTA prefetches its share of the chunk's depth maps into L2 while it sets up (measured: no gain, profiles/tuning_r1.md)
+#endif
 #ifndef MSP_CULL_W_SMEM
 #define MSP_CULL_W_SMEM 0  // 1: keep the chunk's float64 poses in SMEM for the exact path, 0: read them from global
 #endif  // fused object counting keeps a (64 frames x 64 ids) histogram in SMEM
@@ -54,7 +57,8 @@ struct CullFrameConsts {  // per (CTA tile, frame); 128 bytes, all relative to t
   float Bz;               // bound of the Z form
   float ct1, ct0;         // pixel-index guard band  dt = ct1 * rcp(Z) + ct0
   int std_frame;          // bottom row of w2c is exactly [0,0,0,1]
-  int pad[7];
+  int tile_cand;          // 0: the whole 2048-point tile is certainly outside this frame's image
+  int pad[6];
 };
 
 struct CullParams {
@@ -142,6 +146,23 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     if (bulk) bulk_g2s(s_pts, gsrc, bulk, &s_bar);
   }
   if (tid < (int)(bytes - bulk)) s_pts[bulk + tid] = gsrc[bulk + tid];
+#if MSP_CULL_PREFETCH
+  if (MODE == 0 && warp == 1) {
+    // The tiles of one frame chunk are co-resident (blockIdx.x is the fast grid dimension) and all of them gather from
+    // the same nf depth maps a few microseconds from now: pull this CTA's 1/gridDim.x share of those maps into L2 with
+    // bulk prefetches so that the gathers find them there instead of paying the HBM latency.
+    const uint64_t total = (uint64_t)nf * (uint64_t)p.depth_stride * sizeof(uint16_t);
+    const uint64_t slice = ((total + gridDim.x - 1) / gridDim.x + 127u) & ~(uint64_t)127u;
+    const uint64_t lo = (uint64_t)blockIdx.x * slice;
+    const uint64_t hi = (lo + slice < total) ? lo + slice : total;
+    const char* dbase = reinterpret_cast<const char*>(p.depth + (int64_t)f0 * p.depth_stride);
+    constexpr uint32_t kPiece = 16384;
+    for (uint64_t o = lo + (uint64_t)lane * kPiece; o < hi; o += 32ull * kPiece) {
+      const uint32_t sz = (uint32_t)((hi - o < kPiece) ? (hi - o) : kPiece) & ~15u;
+      if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dbase + o), "r"(sz) : "memory");
+    }
+  }
+#endif
 #if MSP_CULL_W_SMEM
   for (int i = tid; i < nf * 16; i += kCullThreads) s_w[i] = p.w2c[(int64_t)f0 * 16 + i];
 #else
@@ -273,11 +294,12 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     M[3] = dh * mag[2] + M[2];
     CullFrameConsts c;
     const double u = 5.9604644775390625e-08, tiny = 1.4210854715202004e-14;  // 2^-24, 2^-46
-    double Bf[5];
+    double Bf[5], top[4];  // top[q]: upper bound of form q over the whole tile (centre value + |a|.extent)
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
       const double dprime = A[q][0] * tc[0] + A[q][1] * tc[1] + A[q][2] * tc[2] + A[q][3];
       const double Aext = fabs(A[q][0]) * ext[0] + fabs(A[q][1]) * ext[1] + fabs(A[q][2]) * ext[2];
+      if (q < 4) top[q] = dprime + Aext;
       Bf[q] = 8.0 * u * (Aext + fabs(dprime)) + tiny * M[q];
       float* dst = (q < 4) ? c.box[q] : c.fz;
       dst[0] = __double2float_rn(A[q][0]), dst[1] = __double2float_rn(A[q][1]), dst[2] = __double2float_rn(A[q][2]);
@@ -293,14 +315,18 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     c.ct1 = __double2float_ru(1.01 * fmax(Bf[0] + dw * Bf[4], Bf[2] + dh * Bf[4]));
     c.ct0 = __double2float_ru(8.0 * u * fmax(dw, dh) + 1e-9);
     c.std_frame = (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
+    // every point of the tile satisfies form_q <= top[q] (exact arithmetic); if that is below -B for some q the whole
+    // tile is outside.  NaN poses: comparisons false -> tile_cand = 0, and indeed nothing is visible.
+    c.tile_cand = (top[0] >= -B) && (top[1] >= -B) && (top[2] >= -B) && (top[3] >= -B);
     if (!c.std_frame && isfinite(B)) {
+      c.tile_cand = 1;
       // perspective row present: the forms are not the image-plane tests — send every point to the exact path
 #pragma unroll
       for (int q = 0; q < 4; ++q) c.box[q][0] = c.box[q][1] = c.box[q][2] = c.box[q][3] = 0.f;
       c.B = finf;
     }
 #pragma unroll
-    for (int i = 0; i < 7; ++i) c.pad[i] = 0;
+    for (int i = 0; i < 6; ++i) c.pad[i] = 0;
     s_c[tid] = c;
   }
   __syncthreads();
@@ -356,13 +382,16 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     uint32_t myword = 0;  // lane j (< 8) ends up holding mask word j of this warp
     uint32_t nq = 0;      // lanes queued for the exact path
 
-    // ---- A: group boxes against the four half-spaces (lane = form q x group g)
-    const float4 a = *reinterpret_cast<const float4*>(c.box[lane >> 3]);
+    // ---- A: group boxes against the four half-spaces (lane = form q x group g); skipped when the whole tile is out
     const float B = c.B;
-    const float v = fmaf(a.x, bcx, fmaf(a.y, bcy, fmaf(a.z, bcz, a.w)));
-    const float r = __fmaf_ru(fabsf(a.x), bhx, __fmaf_ru(fabsf(a.y), bhy, __fmul_ru(fabsf(a.z), bhz)));
-    const uint32_t gb = __ballot_sync(0xffffffffu, __fadd_ru(v, r) >= -B);
-    uint32_t gm = gb & (gb >> 8) & (gb >> 16) & (gb >> 24) & 0xffu;
+    uint32_t gm = 0u;
+    if (c.tile_cand != 0) {
+      const float4 a = *reinterpret_cast<const float4*>(c.box[lane >> 3]);
+      const float v = fmaf(a.x, bcx, fmaf(a.y, bcy, fmaf(a.z, bcz, a.w)));
+      const float r = __fmaf_ru(fabsf(a.x), bhx, __fmaf_ru(fabsf(a.y), bhy, __fmul_ru(fabsf(a.z), bhz)));
+      const uint32_t gb = __ballot_sync(0xffffffffu, __fadd_ru(v, r) >= -B);
+      gm = gb & (gb >> 8) & (gb >> 16) & (gb >> 24) & 0xffu;
+    }
 
     if (gm != 0u) {
       const float4 a0 = *reinterpret_cast<const float4*>(c.box[0]);
@@ -468,10 +497,12 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   }
   if (COUNT) {
     __syncthreads();
-    for (int i = tid; i < nf * p.n_objects; i += kCullThreads) {
-      const int fr = i / p.n_objects, o = i - fr * p.n_objects;
-      const uint32_t v = (s_cnt[fr * kCntWords + ((o + 1) >> 1)] >> (((o + 1) & 1) * 16)) & 0xffffu;
-      if (v != 0u) atomicAdd(p.counts + (int64_t)(f0 + fr) * p.n_objects + o, v);
+    const int o = tid & 63;  // 64 ids per frame row, 4 frame rows per pass
+    if (o < p.n_objects) {
+      for (int fr = tid >> 6; fr < nf; fr += kCullThreads / 64) {
+        const uint32_t v = (s_cnt[fr * kCntWords + ((o + 1) >> 1)] >> (((o + 1) & 1) * 16)) & 0xffffu;
+        if (v != 0u) atomicAdd(p.counts + (int64_t)(f0 + fr) * p.n_objects + o, v);
+      }
     }
   }
   if (p.stats != nullptr) {
