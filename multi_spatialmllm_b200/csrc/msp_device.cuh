@@ -49,7 +49,27 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ uint16_t ldg_u16_nc(const uint16_t* p) { return __ldg(p); }
+#ifndef MSP_GATHER_MODE
+#define MSP_GATHER_MODE 0
+#endif
+// depth-map gather (read-only path).  MSP_GATHER_MODE selects the cache hints (tuning, profiles/tuning_r1.md)
+__device__ __forceinline__ uint16_t ldg_u16_nc(const uint16_t* p) {
+#if MSP_GATHER_MODE == 0
+  return __ldg(p);
+#else
+  uint16_t v;
+#if MSP_GATHER_MODE == 1
+  asm volatile("ld.global.nc.L2::256B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+#elif MSP_GATHER_MODE == 2
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+#elif MSP_GATHER_MODE == 3
+  asm volatile("ld.global.nc.L1::evict_last.L2::128B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+#else
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+#endif
+  return v;
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------
 // camera model
