@@ -178,8 +178,8 @@ def main_reference(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    workers = max(1, min(cores, 192))
-    ppw = args.cpu_pairs_per_worker
+    workers = max(1, min(cores, 64))      # more workers than ~64 lowered the aggregate rate on the GPU host (memory-bound NumPy)
+    ppw = max(1, args.cpu_pairs_per_worker // 3)
     times, pairs_tot = [], 0
     for it in range(args.warmup + args.steps):
         pairs, busy, wall = run_cpu_sample(args.points, ppw, workers, seed0=1000 * it)
@@ -410,7 +410,7 @@ def main_gpu(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
-        workers = max(1, min(cores, 192))
+        workers = max(1, min(cores, 64))
         pairs, busy, wall = run_cpu_sample(args.points, args.cpu_pairs_per_worker, workers)
         line["cpu_baseline"] = {
             "value": pairs / busy, "unit": UNIT, "cores": workers, "host_cores": cores, "kind": "port",

@@ -94,9 +94,10 @@ def test_config4_stress_shape_properties():
         np.testing.assert_array_equal(depth[f], og.depth_to_u16(zb, 1))
         _, _, om = og.frame_visibility(pts.astype(np.float64), s.K, E, depth[f], *s.image_hw)
         np.testing.assert_array_equal(mb[f], om)
-    # every depth pixel that received a point makes exactly its nearest point(s) visible: visible count <= filled pixels
+    # the nearest point of every filled depth pixel passes the strict test against its own render (+ margin), so the
+    # number of visible points is at least the number of filled pixels
     filled = (depth > 0).reshape(32, -1).sum(1)
-    assert (mb.sum(1) <= filled).all() and (mb.sum(1) > 0.5 * filled).all()
+    assert (mb.sum(1) >= filled).all() and (filled > 1000).all()
     pairs = torch.randint(0, 32, (256, 2), dtype=torch.int32)
     rec = sc.records_to_numpy(sc.pair_annotate(pairs, torch.randint(0, 2**31, (256,), dtype=torch.int32), 1))
     for (a, b), r in zip(pairs.tolist(), rec):
