@@ -155,6 +155,13 @@ MSP_API int msp_check_visibility(const double* xy, const double* z, int64_t n, c
 MSP_API int msp_object_counts(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, int32_t F,
                       const uint16_t* instance_ids, int32_t n_objects, uint32_t* counts, void* stream);
 
+/* SOCF:57-65 building block: extents[(f*n_objects + o)*6 + {0,1,2}] = min x,y,z and [+3..5] = max x,y,z (float64) over
+ * the points of object o that are visible in frame f (+inf / -inf when none).  The coverage of a set of frames along an
+ * axis is max(max_f) - min(min_f), which replaces the union-mask passes of find_minimal_combinations (SOCF:76-220). */
+MSP_API int msp_object_extents(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, int32_t F, const void* pts,
+                               int32_t pts_dtype, const uint16_t* instance_ids, int32_t n_objects, double* extents,
+                               void* stream);
+
 /* TAPVid-3D tracks, OM-coord:446-451 + OM-coord:293-315: world = inv(w2c_t) @ [xyz,1]; pinhole projection
  * u = fx*x/(z+1e-8)+cx normalised by W,H; valid iff 0<=u_n<1, 0<=v_n<1, z>0; permille = round_half_even(.*1000).
  *  tracks (T,N,3) float32 camera coordinates, w2c (T,16), fxfycxcy (4) float64 device.

@@ -52,6 +52,7 @@ _SIGNATURES = {
                                       C.POINTER(MspCamera), _P, _P, _P, _P, _P, _P]),
     "msp_check_visibility": (C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(MspCamera), C.c_int32, _P, _P]),
     "msp_object_counts": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]),
+    "msp_object_extents": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "msp_track_project": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "msp_track_pair_displacement": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
 }

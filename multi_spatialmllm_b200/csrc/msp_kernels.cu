@@ -474,6 +474,57 @@ __global__ void __launch_bounds__(256) k_object_counts(const uint32_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-(frame, object) axis-aligned extent of the VISIBLE object points: min/max of x,y,z.
+// single_object_coverage_finder.py:57-65 takes max(coords) - min(coords) over unions of per-image masks; the extent
+// of a union is (max of the per-image maxima) - (min of the per-image minima), so this table replaces every
+// union-mask pass of the coverage search (SOCF:76-220) by scalar look-ups.  One CTA per frame.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long d2ord(double v) {
+  const long long b = __double_as_longlong(v);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double ord2d(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+
+template <int DT>
+__global__ void __launch_bounds__(256) k_object_extents(const uint32_t* __restrict__ mask, int64_t n, int64_t mask_stride,
+                                                        const void* __restrict__ pts, const uint16_t* __restrict__ inst,
+                                                        int n_objects, double* __restrict__ out) {
+  extern __shared__ long long s_ext[];  // [n_objects][6]: min xyz, max xyz as ordered keys
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long kPosInf = d2ord(__longlong_as_double(0x7ff0000000000000LL));
+  const long long kNegInf = d2ord(__longlong_as_double(0xfff0000000000000LL));
+  for (int i = tid; i < n_objects * 6; i += blockDim.x) s_ext[i] = (i % 6 < 3) ? kPosInf : kNegInf;
+  __syncthreads();
+  const uint32_t* row = mask + (int64_t)f * mask_stride;
+  const int nwords = (int)((n + 31) / 32);
+  for (int w0 = warp * 32; w0 < nwords; w0 += (blockDim.x / 32) * 32) {
+    const int wd = w0 + lane;
+    const uint32_t mine = (wd < nwords) ? __ldg(row + wd) : 0u;
+    uint32_t nz = __ballot_sync(0xffffffffu, mine != 0u);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const uint32_t bits = __shfl_sync(0xffffffffu, mine, src);
+      const int64_t pt = (int64_t)(w0 + src) * 32 + lane;
+      if (((bits >> lane) & 1u) && pt < n) {
+        const uint32_t id = __ldg(inst + pt);
+        if (id != 0u && id <= (uint32_t)n_objects) {
+          double x, y, z;
+          PtTraits<DT>::load(pts, pt, x, y, z);
+          long long* e = s_ext + (size_t)(id - 1) * 6;
+          if (x == x && y == y && z == z) {
+            atomicMin(e + 0, d2ord(x)), atomicMin(e + 1, d2ord(y)), atomicMin(e + 2, d2ord(z));
+            atomicMax(e + 3, d2ord(x)), atomicMax(e + 4, d2ord(y)), atomicMax(e + 5, d2ord(z));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n_objects * 6; i += blockDim.x) out[(int64_t)f * n_objects * 6 + i] = ord2d(s_ext[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // TAPVid-3D tracks
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_track_project(const float* __restrict__ tracks, const double* __restrict__ w2c,
@@ -820,6 +871,27 @@ extern "C" int msp_object_counts(const uint32_t* mask_bits, int64_t n, int64_t m
   k_object_counts<<<(unsigned)F, 256, (size_t)(n_objects + 1) * sizeof(uint32_t), (cudaStream_t)stream>>>(
       mask_bits, n, mask_stride_words, instance_ids, n_objects, counts);
   return check_launch("msp_object_counts");
+}
+
+extern "C" int msp_object_extents(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words, int32_t F,
+                                  const void* pts, int32_t pts_dtype, const uint16_t* instance_ids, int32_t n_objects,
+                                  double* extents, void* stream) {
+  REQUIRE(n >= 0 && F >= 0 && n_objects >= 0, "negative size");
+  REQUIRE(n_objects <= 768, "n_objects must be <= 768");
+  REQUIRE(pts_dtype >= 0 && pts_dtype <= 2, "pts_dtype must be 0, 1 or 2");
+  if (F == 0 || n_objects == 0) return MSP_OK;
+  REQUIRE(mask_bits && pts && instance_ids && extents, "msp_object_extents: NULL pointer");
+  REQUIRE(mask_stride_words >= (n + 31) / 32, "mask_stride_words too small");
+  const size_t smem = (size_t)n_objects * 6 * sizeof(long long);
+  cudaStream_t s = (cudaStream_t)stream;
+#define MSP_EXT(DT) k_object_extents<DT><<<(unsigned)F, 256, smem, s>>>(mask_bits, n, mask_stride_words, pts, instance_ids, n_objects, extents)
+  switch (pts_dtype) {
+    case 0: MSP_EXT(0); break;
+    case 1: MSP_EXT(1); break;
+    default: MSP_EXT(2); break;
+  }
+#undef MSP_EXT
+  return check_launch("msp_object_extents");
 }
 
 extern "C" int msp_track_project(const float* tracks, const double* w2c, const double* fxfycxcy, int32_t T, int32_t N,

@@ -213,6 +213,15 @@ class DeviceScene:
         return counts
 
 
+    def object_extents(self) -> torch.Tensor:
+        """(F, n_objects, 6) float64: min xyz / max xyz of each object's visible points per frame (SOCF:57-65)."""
+        assert self.instance_ids is not None and self.num_objects > 0 and self.mask is not None
+        ext = torch.empty((self.F, self.num_objects, 6), dtype=torch.float64, device=self.device)
+        check(lib.msp_object_extents(_ptr(self.mask), self.n, self.stride, self.F, _ptr(self.pts), self.pts_dtype,
+                                     _ptr(self.instance_ids), self.num_objects, _ptr(ext), _stream()), "msp_object_extents")
+        return ext
+
+
 # ------------------------------------------------------------------------------------------------
 # per-scene workers with the reference's return shapes
 # ------------------------------------------------------------------------------------------------

@@ -125,6 +125,31 @@ def main():
                             "answer_values": {k: (v if isinstance(v, (str, list)) else int(v)) for k, v in av.items()},
                             "gt_value": smp["gt_value"] if isinstance(smp["gt_value"], (str, list)) else int(smp["gt_value"])})
         out["camera_movement"] = res
+    # ---- object coverage search (SOCF:76-220) for every object / axis of the fixture scene
+    with quiet:
+        from spatial_engine.object_perception import single_object_coverage_finder as socf
+    with tempfile.TemporaryDirectory() as tmp2, np.errstate(all="ignore"):
+        info_path = ref_layout.write_split([s], tmp2)
+        with quiet:
+            h2 = ref.info_handler.SceneInfoHandler(info_path, posed_images_root=os.path.join(tmp2, "posed_images"),
+                                                   instance_data_root=os.path.join(tmp2, "scannet_instance_data"))
+            _, vis2 = ref.mvi.process_scene(s.scene_id, h2, os.path.join(tmp2, "w.txt"))
+        vdict = {f"{s.scene_id}:image_to_points:{k}": json.dumps(v) for k, v in vis2["image_to_points"].items()}
+        scene_pts = h2.get_scene_points_align(s.scene_id)[:, :3]
+        cov = []
+        for obj in range(s.num_objects):
+            idx = h2.get_object_point_index(s.scene_id, obj)
+            imgs = [k for k, v in vis2["image_to_points"].items() if len(set(v) & set(idx.tolist())) > 0]
+            bbox = h2.get_object_gt_bbox(s.scene_id, obj)
+            for axis in (0, 1, 2):
+                for tol in (0.1, 0.35):
+                    random.seed(0)
+                    with quiet:
+                        sol = socf.find_minimal_combinations(s.scene_id, scene_pts, idx, imgs, vdict, axis, float(bbox[3 + axis]), tol, max_images=5)
+                    cov.append({"object": obj, "axis": axis, "target": float(bbox[3 + axis]), "tolerance": tol, "images": imgs,
+                                "solutions": {str(k): [list(c) for c in v] for k, v in sol.items()}})
+        out["object_coverage"] = cov
+
     # ---- object movement (TAPVid-3D): format_training_samples on the tapvid_small fixture (OM-coord:317-404)
     with quiet:
         from spatial_engine.object_movement import single_object_movement_engine_coord as om

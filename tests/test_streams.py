@@ -153,3 +153,51 @@ def test_object_movement_stream_matches_reference_engine(golden_tapvid, engines_
         nums = [int(v) for v in s["conversations"][1]["value"].replace("The point did not move. ", "").replace("`", " ")
                 .replace("[", " ").replace("]", " ").replace(",", " ").split()]
         assert nums == [w["total_distance"]] + w["xyz"]
+
+
+def _extent_tables(mask, pts, inst, n_obj):
+    """NumPy restatement of msp_object_extents for tests: (F, n_obj, 6) min xyz / max xyz of visible object points."""
+    F = mask.shape[0]
+    ext = np.empty((F, n_obj, 6))
+    ext[..., :3], ext[..., 3:] = np.inf, -np.inf
+    for f in range(F):
+        for o in range(n_obj):
+            sel = mask[f] & (inst == o + 1)
+            if sel.any():
+                ext[f, o, :3], ext[f, o, 3:] = pts[sel].min(0), pts[sel].max(0)
+    return ext
+
+
+def _check_coverage(golden_scannet, engines_golden, ext, rows_of):
+    import random
+    from multi_spatialmllm_b200 import coverage
+    n_sol = 0
+    for it in engines_golden["object_coverage"]:
+        rows = [rows_of[i] for i in it["images"]]
+        lo = [ext[r, it["object"], it["axis"]] for r in rows]
+        hi = [ext[r, it["object"], 3 + it["axis"]] for r in rows]
+        random.seed(0)
+        sol = coverage.find_minimal_combinations(it["images"], lo, hi, it["target"], it["tolerance"], max_images=5)
+        assert {str(k): [list(c) for c in v] for k, v in sol.items()} == it["solutions"], (it["object"], it["axis"])
+        n_sol += sum(len(v) for v in sol.values())
+    assert n_sol > 20
+
+
+def test_coverage_search_matches_reference_cpu(golden_scannet, engines_golden):
+    """Host BFS on extents == the reference's BFS on union masks (SOCF:76-220), extents from a NumPy restatement."""
+    g = golden_scannet
+    valid = [str(v) for v in g["valid_ids"]]
+    ext = _extent_tables(g["ref_mask"], g["points"].astype(np.float64), g["instance_ids"], int(g["num_objects"]))
+    _check_coverage(g, engines_golden, ext, {v: k for k, v in enumerate(valid)})
+
+
+@pytest.mark.gpu
+def test_object_extents_kernel_and_coverage(golden_scannet, engines_golden):
+    g = golden_scannet
+    sc = _scene(g)
+    sc.project_visibility()
+    ext = sc.object_extents().cpu().numpy()
+    ids = [str(v) for v in g["image_ids"]]
+    want = _extent_tables(sc.mask_bool(), g["points"].astype(np.float64), g["instance_ids"], int(g["num_objects"]))
+    np.testing.assert_array_equal(ext, want)                       # exact: min/max select input values
+    _check_coverage(g, engines_golden, ext, {v: k for k, v in enumerate(ids)})
