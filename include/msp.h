@@ -170,6 +170,12 @@ MSP_API int msp_track_project(const float* tracks, const double* w2c, const doub
                       int32_t image_h, int32_t image_w, double* world_out, double* uvn_out, int32_t* permille_out,
                       uint8_t* valid_out, void* stream);
 
+/* OM-coord:49-77 (rigid_body_segmentation's accumulation): condensed_out[pair(i<j) in scipy squareform order] =
+ * sum over t >= 1 of |d_t - d_{t-1}| where it exceeds `smoothing`, d_t = ||track_i(t) - track_j(t)|| (float64).
+ * tracks (T,N,3) float32; condensed_out (N(N-1)/2) float64.  Linkage / fcluster stay on the host. */
+MSP_API int msp_track_cumulative_loss(const float* tracks, int32_t T, int32_t N, double smoothing, double* condensed_out,
+                                      void* stream);
+
 /* OM-coord:484-498 / 329-356 for M (frame1, frame2, track) triples: ||w2-w1||, the displacement expressed in
  * camera-1 axes (w2c[f1] @ [d,0]) and the camera baseline ||c2-c1||.  out (M,5): dist, dx, dy, dz, cam_dist. */
 MSP_API int msp_track_pair_displacement(const double* world, const double* w2c, int32_t T, int32_t N, const int32_t* triples,

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "msp_object_counts": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]),
     "msp_object_extents": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "msp_track_project": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "msp_track_cumulative_loss": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double, _P, _P]),
     "msp_track_pair_displacement": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -561,6 +561,34 @@ __global__ void __launch_bounds__(128) k_track_project(const float* __restrict__
   }
 }
 
+// rigid_body_segmentation's O(T N^2) loop (single_object_movement_engine_coord.py:49-77): for every track pair (i<j)
+// sum over t of |d_t - d_{t-1}| where that change exceeds `smoothing`, d_t = Euclidean distance at frame t (float64,
+// accumulated in frame order like the reference).  One thread per pair; the tracks (T*N*12 B) stay in L2.
+__global__ void __launch_bounds__(256) k_track_cumulative_loss(const float* __restrict__ tracks, int T, int N, double smoothing,
+                                                               double* __restrict__ out) {
+  const int64_t pidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t npairs = (int64_t)N * (N - 1) / 2;
+  if (pidx >= npairs) return;
+  // condensed index (scipy squareform order) -> (i, j), i < j
+  int i = (int)((2.0 * N - 1.0 - sqrt((2.0 * N - 1.0) * (2.0 * N - 1.0) - 8.0 * (double)pidx)) * 0.5);
+  while ((int64_t)i * (2 * N - i - 1) / 2 > pidx) --i;
+  while ((int64_t)(i + 1) * (2 * N - i - 2) / 2 <= pidx) ++i;
+  const int j = (int)(pidx - (int64_t)i * (2 * N - i - 1) / 2) + i + 1;
+  double acc = 0.0, prev = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const float* a = tracks + 3 * ((int64_t)t * N + i);
+    const float* b = tracks + 3 * ((int64_t)t * N + j);
+    const double dx = (double)a[0] - (double)b[0], dy = (double)a[1] - (double)b[1], dz = (double)a[2] - (double)b[2];
+    const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    if (t > 0) {
+      const double ch = fabs(d - prev);
+      if (ch > smoothing) acc = __dadd_rn(acc, ch);
+    }
+    prev = d;
+  }
+  out[pidx] = acc;
+}
+
 __global__ void k_track_pair_displacement(const double* __restrict__ world, const double* __restrict__ w2c, int T, int N,
                                           const int32_t* __restrict__ triples, int64_t M, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -905,6 +933,18 @@ extern "C" int msp_track_project(const float* tracks, const double* w2c, const d
                                                                  (double)image_w, world_out, uvn_out, permille_out,
                                                                  valid_out);
   return check_launch("msp_track_project");
+}
+
+extern "C" int msp_track_cumulative_loss(const float* tracks, int32_t T, int32_t N, double smoothing, double* condensed_out,
+                                         void* stream) {
+  REQUIRE(T >= 0 && N >= 0, "negative size");
+  if (N < 2) return MSP_OK;
+  REQUIRE(tracks && condensed_out, "msp_track_cumulative_loss: NULL pointer");
+  const int64_t npairs = (int64_t)N * (N - 1) / 2;
+  REQUIRE(npairs < (1ll << 31) * 256, "too many track pairs");
+  k_track_cumulative_loss<<<(unsigned)((npairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tracks, T, N, smoothing,
+                                                                                               condensed_out);
+  return check_launch("msp_track_cumulative_loss");
 }
 
 extern "C" int msp_track_pair_displacement(const double* world, const double* w2c, int32_t T, int32_t N,

@@ -301,3 +301,15 @@ class DeviceVideo:
         check(lib.msp_track_pair_displacement(_ptr(self.world), _ptr(self.w2c), self.T, self.N, _ptr(tri),
                                               int(tri.shape[0]), _ptr(out), _stream()), "msp_track_pair_displacement")
         return out
+
+    def rigid_body_groups(self, threshold: float = 0.1, smoothing_factor: float = 0.01, min_size: int = 5):
+        """rigid_body_segmentation + filter_large_groups (OM-coord:49-105): the O(T N^2) accumulation on the GPU,
+        average-linkage clustering of the N x N result on the host (scipy, like the reference)."""
+        from scipy.cluster.hierarchy import fcluster, linkage
+        n = self.N
+        loss = torch.empty((n * (n - 1) // 2,), dtype=torch.float64, device=self.device)
+        check(lib.msp_track_cumulative_loss(_ptr(self.tracks), self.T, n, float(smoothing_factor), _ptr(loss), _stream()),
+              "msp_track_cumulative_loss")
+        labels = fcluster(linkage(loss.cpu().numpy(), method="average"), threshold, criterion="distance")
+        groups = [np.where(labels == i)[0].tolist() for i in range(1, int(labels.max()) + 1)]
+        return [g for g in groups if len(g) > min_size], loss

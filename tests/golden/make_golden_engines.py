@@ -177,6 +177,10 @@ def main():
                     "point_moving": int(e["point_moving"]), "cam_moving": int(e["cam_moving"])})
     out["object_movement"] = res
     out["object_movement_requested"] = [[t["frame1"], t["frame2"], t["point_index"]] for t in trip]
+    # rigid-body segmentation of the camera-frame tracks (OM-coord:49-105), as generate_qa_training_single_scene calls it
+    groups = om.rigid_body_segmentation(tv["tracks_xyz"])
+    out["rigid_body_groups"] = [[int(i) for i in grp] for grp in groups]
+    out["rigid_body_groups_filtered"] = [[int(i) for i in grp] for grp in om.filter_large_groups(groups, min_size=5)]
     with open(os.path.join(HERE, "engines_small.json"), "w") as f:
         json.dump(out, f)
     print({k: len(v) for k, v in out.items()})

@@ -201,3 +201,26 @@ def test_object_extents_kernel_and_coverage(golden_scannet, engines_golden):
     want = _extent_tables(sc.mask_bool(), g["points"].astype(np.float64), g["instance_ids"], int(g["num_objects"]))
     np.testing.assert_array_equal(ext, want)                       # exact: min/max select input values
     _check_coverage(g, engines_golden, ext, {v: k for k, v in enumerate(ids)})
+
+
+@pytest.mark.gpu
+def test_rigid_body_groups_match_reference(golden_tapvid, engines_golden):
+    """GPU accumulation of OM-coord:49-77 + host linkage == the reference's rigid_body_segmentation groups."""
+    from scipy.spatial.distance import pdist
+    from multi_spatialmllm_b200.engine import DeviceVideo
+    g = golden_tapvid
+    vid = DeviceVideo(g["tracks_xyz"], g["w2c"], g["fxfycxcy"], g["image_hw"])
+    groups, loss = vid.rigid_body_groups(min_size=5)
+    assert groups == engines_golden["rigid_body_groups_filtered"]
+    groups_all, _ = vid.rigid_body_groups(min_size=0)
+    assert groups_all == [grp for grp in engines_golden["rigid_body_groups"] if len(grp) > 0]
+    # the accumulated matrix against a NumPy restatement
+    T = g["tracks_xyz"].shape[0]
+    ref = np.zeros(len(loss))
+    prev = pdist(g["tracks_xyz"][0].astype(np.float64))
+    for t in range(1, T):
+        cur = pdist(g["tracks_xyz"][t].astype(np.float64))
+        ch = np.abs(cur - prev)
+        ref += np.where(ch > 0.01, ch, 0)
+        prev = cur
+    np.testing.assert_allclose(loss.cpu().numpy(), ref, rtol=1e-12, atol=1e-14)
