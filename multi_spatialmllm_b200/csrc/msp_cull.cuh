@@ -366,7 +366,13 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     r.unc = (MODE == 0) ? ((cin && !pc) || (!cin && m >= -B)) : (m >= -B);  // z-buffer splats always go exact
     r.zf = Z;
     r.raw = 0u;
+#if defined(MSP_EXPERIMENT_NO_GATHER)
+    if (r.go) r.raw = 60000u;                                   // upper bound experiment: no memory access
+#elif defined(MSP_EXPERIMENT_HOT_GATHER)
+    if (r.go) r.raw = ldg_u16_nc(dm + ((int)di & 4095)) | 0x8000u;  // upper bound experiment: always-cached gather
+#else
     if (r.go) r.raw = ldg_u16_nc(dm + (int)di);
+#endif
     return r;
   };
   auto cmp32 = [&](const Lane32& r, float Bz, bool& vis, bool& unc) {
