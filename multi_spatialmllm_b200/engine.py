@@ -240,13 +240,13 @@ def process_scene_visibility(scene: DeviceScene, image_ids):
         if valid[f]:
             image_to_points[image_id] = np.flatnonzero(m[f]).tolist()
     ids = np.asarray(image_ids)
-    point_to_images = {}
-    mv = m[valid]
-    idv = ids[valid]
+    mv, idv = m[valid], ids[valid]
     order = np.argsort(idv, kind="stable")          # sorted(list(set)) of string ids (MVI:116-118)
     mv, idv = mv[order], idv[order]
-    for p in range(scene.n):
-        point_to_images[p] = idv[mv[:, p]].tolist()
+    # all (point, frame) incidences at once, grouped by point; points never seen keep an empty list (MVI:116-118)
+    p_idx, f_idx = np.nonzero(mv.T)
+    cuts = np.cumsum(np.bincount(p_idx, minlength=scene.n))[:-1]
+    point_to_images = dict(enumerate(a.tolist() for a in np.split(idv[f_idx], cuts)))
     return {"image_to_points": image_to_points, "point_to_images": point_to_images}
 
 
