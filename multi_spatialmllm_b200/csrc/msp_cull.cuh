@@ -73,6 +73,8 @@ struct CullParams {
   int64_t mask_stride;
   Intrinsics K;
   ImageGeom g;
+  float fdw, fdh, fdw1, fdh1;  // depth_w, depth_h, depth_w-1, depth_h-1 as float32 (exact), kept in the constant bank
+  float fscale;               // float32 rounding of depth_scale (its error is inside the 6u d guard)
   const uint16_t* inst;       // optional (n): 1-indexed instance ids for fused per-(frame, object) counts
   uint32_t* counts;           // optional (F, n_objects), zeroed by the caller; accumulated with atomics
   int32_t n_objects;          // <= kCullMaxObjects when counts != NULL
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   __shared__ __align__(16) CullFrameConsts s_c[kCullFramesPerCta];
   __shared__ uint32_t s_words[kCullWarps][kCullPtsPerLane];
   __shared__ uint8_t s_q[kCullWarps][kCullWarpPoints];
+  __shared__ uint8_t s_flist[kCullFramesPerCta];  // frames of this chunk in which the tile may be visible
+  __shared__ int s_nlist;
   __shared__ int s_red[9];  // ordered-int min xyz, max xyz, then uint max |x'|,|y'|,|z'|
   __shared__ __align__(8) uint64_t s_bar;
 
@@ -334,9 +338,8 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   const int64_t word0 = (int64_t)blockIdx.x * (kCullTilePoints / 32) + warp * kCullPtsPerLane;
   const uint32_t lt = (1u << lane) - 1u;
   const bool word_ok = (lane < kCullPtsPerLane) && (word0 + lane < p.mask_stride);
-  uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;  // advanced by one row per frame
-  const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h;
-  const float fdw1 = fdw - 1.0f, fdh1 = fdh - 1.0f;
+  uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;
+  const float* s_lane = s_rel + 3 * (warp * kCullWarpPoints + lane);  // this lane's point of group j is at s_lane + 96 j
   unsigned int st_f32 = 0, st_exact = 0;
 
   // float32 evaluation of one group's point on this lane (branch-free; see the header comment for the bounds)
@@ -347,12 +350,12 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   };
   auto eval32 = [&](int j, const float4& a0, const float4& a2, const float4& az, float B, float B2, float ct1,
                     float half_ct0, const uint16_t* dm) -> Lane32 {
-    const float* q = s_rel + 3 * (warp * kCullWarpPoints + j * 32 + lane);
+    const float* q = s_lane + 96 * j;
     const float x = q[0], y = q[1], z = q[2];
     const float I0 = fmaf(a0.x, x, fmaf(a0.y, y, fmaf(a0.z, z, a0.w)));
     const float I1 = fmaf(a2.x, x, fmaf(a2.y, y, fmaf(a2.z, z, a2.w)));
     const float Z = fmaf(az.x, x, fmaf(az.y, y, fmaf(az.z, z, az.w)));
-    const float Q1 = fmaf(fdw, Z, -I0), Q3 = fmaf(fdh, Z, -I1);
+    const float Q1 = fmaf(p.fdw, Z, -I0), Q3 = fmaf(p.fdh, Z, -I1);
     const float m = fminf(fminf(I0, Q1), fminf(I1, Q3));  // NaN only for empty / non-finite slots: never visible
     const bool cin = m >= B2;                               // certainly inside the image, in front of the camera
     const float rz = rcp_approx(Z);
@@ -360,10 +363,10 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     const float ix = rintf(tx), iy = rintf(ty);
     const float e = fmaxf(fabsf(tx - ix), fabsf(ty - iy));
     const bool pc = e <= fmaf(-ct1, rz, half_ct0);          // the reference rounds to the same depth pixel
-    const float di = fmaf(fminf(iy, fdh1), fdw, fminf(ix, fdw1));
+    const float di = fmaf(fminf(iy, p.fdh1), p.fdw, fminf(ix, p.fdw1));
     Lane32 r;
     r.go = (MODE == 0) && cin && pc;
-    r.unc = (MODE == 0) ? ((cin && !pc) || (!cin && m >= -B)) : (m >= -B);  // z-buffer splats always go exact
+    r.unc = (m >= -B) && !r.go;  // not provably outside and not decided here (z-buffer splats: always the exact path)
     r.zf = Z;
     r.raw = 0u;
 #if defined(MSP_EXPERIMENT_NO_GATHER)
@@ -376,13 +379,29 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     return r;
   };
   auto cmp32 = [&](const Lane32& r, float Bz, bool& vis, bool& unc) {
-    const float d = (float)r.raw * (float)p.g.depth_scale;
-    const float mz = fmaf(3.6e-7f, d, Bz);  // 6u d + B_Z: d^ is within 2.1u d of raw*0.001, plus the rounding of d -/+ mz
-    vis = r.go && (r.zf < d - mz);
-    unc = r.go && !vis && !(r.zf >= d + mz);
+    const float d = (float)r.raw * p.fscale;
+    const float mz = fmaf(3.6e-7f, d, Bz);  // 6u d + B_Z: d^ is within 2.1u d of raw*0.001, plus the rounding of z^ - d^
+    const float t = r.zf - d;
+    vis = r.go && (t < -mz);
+    unc = r.go && (fabsf(t) <= mz);
   };
 
-  for (int fi = 0; fi < nf; ++fi) {
+  // frames in which the whole tile is certainly outside the image: their mask words are zero, nothing else to do
+  if (tid == 0) {
+    int k = 0;
+    for (int fi = 0; fi < nf; ++fi)
+      if (s_c[fi].tile_cand != 0) s_flist[k++] = (uint8_t)fi;
+    s_nlist = k;
+  }
+  if (MODE == 0 && word_ok) {
+    for (int fi = 0; fi < nf; ++fi)
+      if (s_c[fi].tile_cand == 0) mask_ptr[(int64_t)fi * p.mask_stride] = 0u;
+  }
+  __syncthreads();
+  const int nlist = s_nlist;
+
+  for (int li = 0; li < nlist; ++li) {
+    const int fi = s_flist[li];
     const CullFrameConsts& c = s_c[fi];
     const int64_t f = f0 + fi;
     uint32_t myword = 0;  // lane j (< 8) ends up holding mask word j of this warp
@@ -391,7 +410,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     // ---- A: group boxes against the four half-spaces (lane = form q x group g); skipped when the whole tile is out
     const float B = c.B;
     uint32_t gm = 0u;
-    if (c.tile_cand != 0) {
+    {
       const float4 a = *reinterpret_cast<const float4*>(c.box[lane >> 3]);
       const float v = fmaf(a.x, bcx, fmaf(a.y, bcy, fmaf(a.z, bcz, a.w)));
       const float r = __fmaf_ru(fabsf(a.x), bhx, __fmaf_ru(fabsf(a.y), bhy, __fmul_ru(fabsf(a.z), bhz)));
@@ -477,8 +496,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       __syncwarp();
     }
     if (MODE == 0) {
-      if (word_ok) *mask_ptr = myword;
-      mask_ptr += p.mask_stride;
+      if (word_ok) mask_ptr[(int64_t)fi * p.mask_stride] = myword;
       if (COUNT) {
         // lanes 0..7 hold the final words; uniform groups: one shared-memory add per non-empty word
         const bool mine_uni = (lane < kCullPtsPerLane) && ((uni_mask >> lane) & 1u);

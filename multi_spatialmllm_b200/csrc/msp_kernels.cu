@@ -669,6 +669,8 @@ static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool m
     c.pts = p.pts, c.n = p.n, c.w2c = p.w2c, c.F = p.F, c.depth = p.depth, c.zbuf = p.zbuf;
     c.depth_stride = p.depth_stride, c.mask = p.mask, c.mask_stride = p.mask_stride, c.K = p.K, c.g = p.g;
     c.stats = g_cull_stats;
+    c.fdw = (float)p.g.depth_w, c.fdh = (float)p.g.depth_h, c.fdw1 = c.fdw - 1.0f, c.fdh1 = c.fdh - 1.0f;
+    c.fscale = (float)p.g.depth_scale;
     c.inst = p.inst, c.counts = p.counts, c.n_objects = p.n_objects;
     const bool count = (MODE == MODE_VIS) && p.counts != nullptr;
 #define MSP_CULL_LAUNCH(DT, CNT)                                                                             \
