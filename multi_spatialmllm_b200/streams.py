@@ -236,6 +236,42 @@ def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="
     return out
 
 
+def object_perception_samples(scene_id, image_hw, dimension_name, object_dims_m, object_categories, coverage_by_object,
+                              max_k=6, templates=None, rng=None):
+    """single_object_perception_engine.build_lwh_qa_samples (SOPE:129-227) for one scene.
+
+    coverage_by_object: {object_id: {k: [image-id tuples]}} for this dimension (tables.object_coverage_scene);
+    object_dims_m / object_categories: {object_id: metres} / {object_id: raw category}.  gt_value = int(round(m*1000)).
+    Returns {k: [samples]}; the image order inside a combination is shuffled like the reference (SOPE:188)."""
+    tp = (templates or Templates()).t.get("object_perception", {
+        "task": ["Use the images to estimate the size of the object."],
+        "questions": ["What is the {dimension} of the {object_category} in millimetres?"],
+        "answers": ["`{value_mm}`"]})
+    rng = rng or np.random.default_rng(0)
+    H, W = image_hw
+    out = {k: [] for k in range(1, max_k + 1)}
+    for object_id, k_dict in coverage_by_object.items():
+        val_mm = int(round(float(object_dims_m[object_id]) * 1000))
+        cat = object_categories[object_id]
+        for k_key, combos in k_dict.items():
+            k = int(k_key)
+            if k < 1 or k > max_k:
+                continue
+            for ci, combo in enumerate(combos):
+                if not combo:
+                    continue
+                combo = [combo[i] for i in rng.permutation(len(combo))]
+                prefix = "\n".join(f"Image-{i}: <image>" for i in range(1, len(combo) + 1))
+                q = _pick(rng, tp["questions"]).format(dimension=dimension_name, object_category=cat)
+                ans = _pick(rng, tp["answers"]).format(dimension=dimension_name, value_mm=val_mm, object_category=cat)
+                out[k].append({"id": f"{scene_id}_{object_id}_{k}_{ci}", "image": [f"{scene_id}/{img}.jpg" for img in combo],
+                               "conversations": [{"from": "human", "value": f"{prefix}\n{_pick(rng, tp['task'])}\n{q}"},
+                                                 {"from": "gpt", "value": ans}],
+                               "height_list": [H] * len(combo), "width_list": [W] * len(combo),
+                               "question_type": f"object_perception_{dimension_name}_estimation", "gt_value": val_mm})
+    return out
+
+
 def to_eval_sample(sample: dict) -> dict:
     """DE-coor / VC-coor / CME convert_train_sample_to_eval_sample: the first human turn becomes ``text``."""
     s = dict(sample)

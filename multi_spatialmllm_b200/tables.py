@@ -143,3 +143,31 @@ def run_object_visibility_split(scene_infos, output_pkl: str, scene_ids=None, de
     with open(output_pkl, "wb") as f:
         pickle.dump(out, f)
     return out
+
+
+COVERAGE_TOLERANCE = 0.1        # single_object_coverage_finder.py TOLERANCE
+
+
+def object_coverage_scene(scene_infos, scene_id: str, sc: "engine.DeviceScene", image_ids, object_visibility: dict,
+                          max_images: int = 5) -> dict:
+    """single_object_coverage_finder.process_scene_for_coverage (SOCF:267-284) with process_object (SOCF:222-265):
+    per object {"height" | "length" | "width": {k: [image-id tuples]}}, using one msp_object_extents pass for the scene
+    instead of union masks.  Uses the global ``random`` state like the reference (seed it the same way)."""
+    from . import coverage
+    sc.project_visibility()
+    ext = sc.object_extents().cpu().numpy()                      # (F, n_obj, 6)
+    row = {img: f for f, img in enumerate(image_ids)}
+    out = {}
+    for object_id, vis_list in object_visibility["object_to_images"].items():
+        imgs = [v["image_id"] for v in vis_list]
+        rows = [row[i] for i in imgs]
+        width_axis = scene_infos.get_object_width_axis_aligned(scene_id, object_id)
+        plan = (("height", 2, scene_infos.get_object_height(scene_id, object_id)),
+                ("length", 1 if width_axis == 0 else 0, scene_infos.get_object_length(scene_id, object_id)),
+                ("width", width_axis, scene_infos.get_object_width(scene_id, object_id)))
+        res = {}
+        for name, axis, target in plan:
+            res[name] = coverage.find_minimal_combinations(imgs, ext[rows, object_id, axis], ext[rows, object_id, 3 + axis],
+                                                           float(target), COVERAGE_TOLERANCE, max_images=max_images)
+        out[object_id] = res
+    return out

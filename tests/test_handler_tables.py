@@ -142,3 +142,45 @@ def test_split_drivers_write_reference_tables(disk_scene, golden_scannet, tmp_pa
         want = og.object_visibility_rows(counts, totals)
         got = [(e["object_id"], e["intersection_count"], e["visibility"]) for e in ov["image_to_objects"].get(str(image_id), [])]
         assert got == want
+
+
+@pytest.mark.gpu
+def test_object_coverage_and_perception_stream(disk_scene, golden_scannet):
+    """Scene-level coverage driver (SOCF:222-284) + object_perception writer (SOPE:129-227) on the golden scene;
+    the BFS itself is pinned to the reference in tests/test_streams.py."""
+    import json
+    import random
+    from multi_spatialmllm_b200 import coverage, streams, tables
+    s, root, info = disk_scene
+    h = _handler(root, info)
+    sc, image_ids = tables.device_scene_from_handler(h, s.scene_id)
+    ov = tables.object_visibility_scene(h, s.scene_id, sc, image_ids)
+    random.seed(0)
+    cov = tables.object_coverage_scene(h, s.scene_id, sc, image_ids, ov)
+    assert set(cov) == set(ov["object_to_images"])
+    mb = sc.mask_bool()
+    pts = golden_scannet["points"].astype(np.float64)
+    inst = golden_scannet["instance_ids"]
+    n_checked = 0
+    for obj, res in cov.items():
+        for name, axis, target in (("height", 2, h.get_object_height(s.scene_id, obj)),):
+            for k, combos in res[name].items():
+                for combo in combos:
+                    union = np.zeros(len(pts), bool)
+                    for img in combo:
+                        union |= mb[image_ids.index(img)]
+                    sel = union & (inst == obj + 1)
+                    covv = pts[sel][:, axis].max() - pts[sel][:, axis].min()       # SOCF:57-65 on the union mask
+                    assert coverage.covers_dimension(covv, target, 0.1) and len(combo) == k
+                    n_checked += 1
+    assert n_checked > 3
+    dims = {o: h.get_object_height(s.scene_id, o) for o in cov}
+    cats = {o: h.get_object_raw_category(s.scene_id, o) for o in cov}
+    out = streams.object_perception_samples(s.scene_id, h.get_image_shape(s.scene_id), "height", dims, cats,
+                                            {o: r["height"] for o, r in cov.items()})
+    flat = [x for v in out.values() for x in v]
+    assert len(flat) == n_checked
+    for x in flat:
+        o = int(x["id"].split("_")[2])
+        assert x["gt_value"] == int(round(dims[o] * 1000)) and x["question_type"] == "object_perception_height_estimation"
+        assert len(x["image"]) == len(x["height_list"]) == int(x["id"].split("_")[3]) and json.dumps(x)
