@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     uint32_t raw;
     bool go, unc;
   };
+  const double* wz = nullptr;      // MODE 1: row 2 of the current frame's w2c (float64) and its z-buffer row
+  unsigned int* zrow = nullptr;
   auto eval32 = [&](int j, const float4& a0, const float4& a2, const float4& az, float B, float B2, float ct1,
                     float half_ct0, const uint16_t* dm) -> Lane32 {
     const float* q = s_lane + 96 * j;
@@ -365,10 +367,23 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     const bool pc = e <= fmaf(-ct1, rz, half_ct0);          // the reference rounds to the same depth pixel
     const float di = fmaf(fminf(iy, p.fdh1), p.fdw, fminf(ix, p.fdw1));
     Lane32 r;
-    r.go = (MODE == 0) && cin && pc;
-    r.unc = (m >= -B) && !r.go;  // not provably outside and not decided here (z-buffer splats: always the exact path)
+    r.go = cin && pc;
+    r.unc = (m >= -B) && !r.go;  // not provably outside and not decided here
     r.zf = Z;
     r.raw = 0u;
+    if (MODE == 1) {
+      // z-buffer splat: the pixel is certain, the stored value must be float32(z_ref) — recompute z alone in float64
+      // from the original coordinates (IH:60,63 operation order) and splat; nothing is left to compare later
+      if (r.go) {
+        const int idx = warp * kCullWarpPoints + j * 32 + lane;
+        double x64, y64, z64;
+        PtTraits<DT>::load(p.pts, base + idx, x64, y64, z64);
+        const double zref = row_dot_h(wz, x64, y64, z64);
+        atomicMin(zrow + (int)di, __float_as_uint(__double2float_rn(zref)));
+      }
+      r.go = false;
+      return r;
+    }
 #if defined(MSP_EXPERIMENT_NO_GATHER)
     if (r.go) r.raw = 60000u;                                   // upper bound experiment: no memory access
 #elif defined(MSP_EXPERIMENT_HOT_GATHER)
@@ -424,6 +439,10 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       const float4 az = *reinterpret_cast<const float4*>(c.fz);
       const float B2 = B + B, ct1 = c.ct1, half_ct0 = 0.5f - c.ct0, Bz = c.Bz;
       const uint16_t* dm = p.depth + f * p.depth_stride;
+      if (MODE == 1) {
+        wz = s_w + fi * 16 + 8;
+        zrow = reinterpret_cast<unsigned int*>(p.zbuf + f * p.depth_stride);
+      }
       if (p.stats != nullptr) st_f32 += __popc(gm);
       // ---- B + C: candidate groups two at a time (two independent dependency chains per lane), then a leftover
       while (gm & (gm - 1u)) {
