@@ -12,7 +12,8 @@
 //
 //   Coordinates are re-centred on the tile centre c (x' = fl(x - c)); each affine form F(p) = a.p + d of
 //   DESIGN.md §3 is evaluated as fl(a0 x' + fl(a1 y' + fl(a2 z' + d'))), d' = fl32(a.c + d) formed in float64.
-//   Sources of error: coefficient rounding 1u, re-centring 1u, float64->float32 input rounding 1u, three FMA
+//   (float64 inputs are re-centred in float64 and rounded once.)  Sources of error: coefficient rounding 1u,
+//   re-centring / input rounding 1u (+1u slack), three FMA
 //   roundings 3u on the a.x' part; 1u + 3u on d'.  Hence |F^ - F| <= 6u (A_F + |d'_F|), A_F = sum |a_k| ext_k,
 //   ext_k = max_tile |x'_k|.  We use B_F = 8u (A_F + |d'_F|) + 2^-46 M_F (M_F = un-cancelled magnitude, covering the
 //   float64 evaluation of d' and the reference's own float64 rounding).  Forms (already scaled to depth pixels,
@@ -237,7 +238,20 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     float ex = 0.f, ey = 0.f, ez = 0.f;
 #pragma unroll
     for (int j = 0; j < kCullPtsPerLane; ++j) {
-      px[j] -= tcx, py[j] -= tcy, pz[j] -= tcz;  // NaN stays NaN
+      if (DT == 2) {
+        // float64 inputs: subtract the centre in float64 and round ONCE, so that the error of x' is u |x'| and not
+        // u |x| (rounding the coordinate itself to float32 first loses |x| * 2^-24: metres at kilometre offsets)
+        if (px[j] == px[j]) {
+          const int idx = warp * kCullWarpPoints + j * 32 + lane;
+          double x64, y64, z64;
+          PtTraits<DT>::load(s_pts, idx, x64, y64, z64);
+          px[j] = __double2float_rn(x64 - (double)tcx);
+          py[j] = __double2float_rn(y64 - (double)tcy);
+          pz[j] = __double2float_rn(z64 - (double)tcz);
+        }
+      } else {
+        px[j] -= tcx, py[j] -= tcy, pz[j] -= tcz;  // NaN stays NaN
+      }
       const bool ok = px[j] == px[j];
       ex = fmaxf(ex, fabsf(px[j])), ey = fmaxf(ey, fabsf(py[j])), ez = fmaxf(ez, fabsf(pz[j]));  // fmaxf ignores NaN
       const float lx = ok ? px[j] : finf, ly = ok ? py[j] : finf, lz = ok ? pz[j] : finf;

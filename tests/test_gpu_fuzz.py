@@ -74,7 +74,7 @@ def _case(seed):
     return dict(pts=dev_pts, K=K, c2w=c2w, A=A, hw=(H, W), dhw=(dh, dw), depth_scale=depth_scale, inst=inst, rng=rng)
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(64))
 def test_fast_path_equals_reference_order_kernel(seed, monkeypatch):
     import torch
     from multi_spatialmllm_b200.engine import DeviceScene
