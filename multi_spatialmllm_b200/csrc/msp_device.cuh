@@ -205,39 +205,68 @@ __device__ inline void matmul4(const double* A, const double* B, double* C) {
     }
 }
 
-// inverse by LU with partial pivoting and two triangular solves against the identity (the LAPACK gesv
-// recipe np.linalg.inv follows).  Returns false for a singular matrix.
+// 4x4 inverse in EXACTLY the operation order of np.linalg.inv as built on OpenBLAS (dgesv = getrf + getrs):
+//   * left-looking LU (getf2): column j first receives the earlier row swaps, then every entry has the dot product of
+//     the already factored part subtracted — the dot is accumulated from 0 with FMAs in ascending k and subtracted once;
+//     pivot = first largest |.| on or below the diagonal; the sub-diagonal is scaled by the RECIPROCAL of the pivot;
+//   * forward substitution with fma(-l, y, s) in ascending k;
+//   * back substitution with fma(-u, x, s) in DESCENDING k and a multiplication by the reciprocal of the diagonal.
+// Found by exhaustive search over the plausible orders with exact-FMA emulation and verified bit-for-bit against
+// np.linalg.inv on 1 860 matrices (ScanNet-like poses, TAPVid w2c, random affine and general matrices with pivoting,
+// kilometre-scale translations): tests/test_oracle_golden.py::test_device_inverse_order_matches_numpy restates it.
+// Returns false for a singular matrix.
 __device__ inline bool inverse4(const double* M, double* inv) {
   double a[16];
-  int perm[4] = {0, 1, 2, 3};
+  int perm[4] = {0, 1, 2, 3}, ipiv[4] = {0, 1, 2, 3};
   for (int i = 0; i < 16; ++i) a[i] = M[i];
-  for (int c = 0; c < 4; ++c) {
-    int piv = c;
-    double best = fabs(a[c * 4 + c]);
-    for (int r = c + 1; r < 4; ++r) {
-      const double v = fabs(a[r * 4 + c]);
-      if (v > best) best = v, piv = r;
-    }
-    if (!(best > 0.0)) return false;
-    if (piv != c) {
-      for (int k = 0; k < 4; ++k) {
-        const double t = a[c * 4 + k];
-        a[c * 4 + k] = a[piv * 4 + k];
-        a[piv * 4 + k] = t;
+  for (int j = 0; j < 4; ++j) {
+    double b[4];
+    for (int i = 0; i < 4; ++i) b[i] = a[i * 4 + j];
+    for (int i = 0; i < j; ++i) {
+      const int ip = ipiv[i];
+      if (ip != i) {
+        const double t = b[i];
+        b[i] = b[ip];
+        b[ip] = t;
       }
-      const int t = perm[c];
-      perm[c] = perm[piv];
-      perm[piv] = t;
     }
-    const double rp = __ddiv_rn(1.0, a[c * 4 + c]);
-    for (int r = c + 1; r < 4; ++r) {
-      const double l = __dmul_rn(a[r * 4 + c], rp);
-      a[r * 4 + c] = l;
-      for (int k = c + 1; k < 4; ++k) a[r * 4 + k] = __fma_rn(-l, a[c * 4 + k], a[r * 4 + k]);
+    for (int i = 1; i < j; ++i) {
+      double acc = 0.0;
+      for (int k = 0; k < i; ++k) acc = __fma_rn(a[i * 4 + k], b[k], acc);
+      b[i] = __dsub_rn(b[i], acc);
     }
+    for (int r = j; r < 4; ++r) {
+      double acc = 0.0;
+      for (int k = 0; k < j; ++k) acc = __fma_rn(a[r * 4 + k], b[k], acc);
+      b[r] = __dsub_rn(b[r], acc);
+    }
+    int jp = j;
+    double best = fabs(b[j]);
+    for (int r = j + 1; r < 4; ++r) {
+      const double v = fabs(b[r]);
+      if (v > best) best = v, jp = r;
+    }
+    ipiv[j] = jp;
+    if (!(best > 0.0)) return false;
+    if (jp != j) {
+      const double t = b[j];
+      b[j] = b[jp];
+      b[jp] = t;
+      for (int k = 0; k < j; ++k) {
+        const double u = a[j * 4 + k];
+        a[j * 4 + k] = a[jp * 4 + k];
+        a[jp * 4 + k] = u;
+      }
+      const int tp = perm[j];
+      perm[j] = perm[jp];
+      perm[jp] = tp;
+    }
+    const double rp = __ddiv_rn(1.0, b[j]);
+    for (int r = j + 1; r < 4; ++r) b[r] = __dmul_rn(b[r], rp);
+    for (int i = 0; i < 4; ++i) a[i * 4 + j] = b[i];
   }
   for (int j = 0; j < 4; ++j) {  // solve L U x = P e_j
-    double y[4];
+    double y[4], x[4];
     for (int i = 0; i < 4; ++i) {
       double s = (perm[i] == j) ? 1.0 : 0.0;
       for (int k = 0; k < i; ++k) s = __fma_rn(-a[i * 4 + k], y[k], s);
@@ -245,9 +274,10 @@ __device__ inline bool inverse4(const double* M, double* inv) {
     }
     for (int i = 3; i >= 0; --i) {
       double s = y[i];
-      for (int k = i + 1; k < 4; ++k) s = __fma_rn(-a[i * 4 + k], inv[k * 4 + j], s);
-      inv[i * 4 + j] = __ddiv_rn(s, a[i * 4 + i]);
+      for (int k = 3; k > i; --k) s = __fma_rn(-a[i * 4 + k], x[k], s);
+      x[i] = __dmul_rn(s, __ddiv_rn(1.0, a[i * 4 + i]));
     }
+    for (int i = 0; i < 4; ++i) inv[i * 4 + j] = x[i];
   }
   return true;
 }

@@ -41,8 +41,10 @@ def test_golden_projection_and_masks(golden_scannet, layout):
     np.testing.assert_array_equal(sc.E.cpu().numpy().reshape(-1, 4, 4)[rows], g["ref_E_aligned"])
     np.testing.assert_array_equal(mb[rows], g["ref_mask"])
     xy, z = xy.cpu().numpy(), z.cpu().numpy()
-    np.testing.assert_allclose(xy[rows], g["ref_xy"], rtol=RTOL, atol=1e-7)
-    np.testing.assert_allclose(z[rows], g["ref_z"], rtol=RTOL, atol=1e-9)
+    # bit-identical floats: the device reproduces NumPy's operation order for E = A @ c2w, inv(E) (LAPACK gesv order),
+    # both 4-term matrix products (k-sequential FMA chains) and the IEEE division — no tolerance needed on the fixture
+    np.testing.assert_array_equal(xy[rows], g["ref_xy"])
+    np.testing.assert_array_equal(z[rows], g["ref_z"])
     invalid = sorted(set(range(len(g["image_ids"]))) - set(rows))
     assert invalid and not mb[invalid].any()                       # -inf poses see nothing
     np.testing.assert_array_equal(sc.valid.cpu().numpy()[invalid], 0)
@@ -382,3 +384,33 @@ def test_cull_path_equals_reference_order_path(layout, monkeypatch):
         E = og.aligned_pose(s.axis_align, s.c2w[f])
         _, _, om = og.frame_visibility(p64, s.K, E, depth_ref[f], *s.image_hw)
         np.testing.assert_array_equal(mb[f], om)
+
+
+def test_pose_prologue_is_bit_identical_to_numpy_fixture():
+    """k_pose_prepare: aligned pose = axis_align @ c2w and its inverse, against np.linalg.inv values committed from the
+    build container (tests/golden/inverse_small.npz) — exact equality, no tolerance."""
+    import os
+    import torch
+    from multi_spatialmllm_b200._lib import check, lib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "inverse_small.npz"))
+    dev = "cuda:0"
+
+    def prep(mats, A):
+        F = len(mats)
+        c2w = torch.from_numpy(np.ascontiguousarray(mats.reshape(F, 16))).to(dev)
+        Ad = None if A is None else torch.from_numpy(np.ascontiguousarray(A.reshape(16))).to(dev)
+        E = torch.empty((F, 16), dtype=torch.float64, device=dev)
+        w = torch.empty((F, 16), dtype=torch.float64, device=dev)
+        yp = torch.empty((F, 2), dtype=torch.float64, device=dev)
+        v = torch.empty((F,), dtype=torch.int32, device=dev)
+        check(lib.msp_pose_prepare(c2w.data_ptr(), None if Ad is None else Ad.data_ptr(), F, E.data_ptr(), w.data_ptr(),
+                                   yp.data_ptr(), v.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return E.cpu().numpy().reshape(F, 4, 4), w.cpu().numpy().reshape(F, 4, 4), v.cpu().numpy()
+
+    _, w, v = prep(g["mats"], None)
+    assert v.all()
+    np.testing.assert_array_equal(w, g["inv"])
+    n = len(g["aligned"])
+    E, w, _ = prep(g["mats"][:n], g["axis_align"])
+    np.testing.assert_array_equal(E, g["aligned"])
+    np.testing.assert_array_equal(w, g["aligned_inv"])
