@@ -174,18 +174,24 @@ def test_annotation_integers_on_rounding_boundaries():
     frames = np.repeat(np.arange(4), 300)
     a = sc.annotate_points(np.arange(len(pts)), frames)
     pm, mm, pix, vis = (a[k].cpu().numpy() for k in ("permille", "depth_mm", "pix", "visible"))
-    n_ok = 0
+    # does this machine's NumPy use the same inverse order as the committed fixture (and hence as the device)?
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "inverse_small.npz"))
+    numpy_matches_fixture = np.array_equal(np.linalg.inv(g["mats"]), g["inv"])
+    n_ok = n_off = 0
     for i, f in enumerate(frames):
         r = og.annotate_point(pts[i], s.K, E[f], np.full((480, 640), 65535, np.uint16), H, W)
         if r is None:
             assert not vis[i]
             continue
-        # the device inverse differs from LAPACK's by a few ulps, which may legitimately move a value across a boundary
-        # it sits on to within ~1e-13; accept only exact equality or a documented +-1 with a boundary distance < 1e-9
         for got, want, val in ((pm[i][0], r["x_permille"], r["u"] / W * 1000), (pm[i][1], r["y_permille"], r["v"] / H * 1000),
                                (mm[i], r["depth_mm"], r["z"] * 1000)):
             if got != want:
+                # only legitimate when the host BLAS differs from the device order in the last ulp of inv(E) AND the value
+                # sits on the boundary to within that ulp
                 assert abs(got - want) == 1 and abs(abs(val - np.floor(val)) - 0.5) < 1e-9
+                n_off += 1
             else:
                 n_ok += 1
-    assert n_ok > 3000
+    assert n_ok > 2000
+    if numpy_matches_fixture:
+        assert n_off == 0, f"{n_off} boundary values differ although the host inverse order equals the device order"
