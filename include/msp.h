@@ -137,8 +137,14 @@ MSP_API int msp_pair_annotate(const uint32_t* mask_bits, int64_t n, int64_t mask
                       const double* host_K16, const double* E, const double* w2c, const double* yawpitch,
                       const uint16_t* depth, const msp_camera* host_cam, msp_pair_record* records, void* stream);
 
+/* IH:46-72 for n points and ONE pose: uvz (n,3) float64 = (u, v, depth).  Uses the operation order NumPy applies to this
+ * shape: the N >= 2 matrix-matrix order for n >= 2, the single-column order for n == 1 (they differ in the last ulp). */
+MSP_API int msp_project_points(const void* pts, int64_t n, int32_t pts_dtype, const double* host_K16, const double* w2c_one,
+                               double* uvz, void* stream);
+
 /* IH:291-305 (+ the integer maths of DE-dot:216-218,261) for M (point, frame) requests.
- * uvz (M,3) float64; permille (M,2), depth_mm (M), pix (M,2) int32; visible (M) uint8.  Any output may be NULL. */
+ * uvz (M,3) float64; permille (M,2), depth_mm (M), pix (M,2) int32; visible (M) uint8.  Any output may be NULL.
+ * Every request is evaluated in the single-column matmul order of the reference's per-point calls. */
 MSP_API int msp_annotate_points(const void* pts, int64_t n, int32_t pts_dtype, const int32_t* point_ids,
                         const int32_t* frame_ids, int64_t M, const double* host_K16, const double* w2c,
                         const uint16_t* depth, const msp_camera* host_cam, double* uvz, int32_t* permille,

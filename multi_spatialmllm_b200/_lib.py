@@ -48,6 +48,7 @@ _SIGNATURES = {
     "msp_pair_overlap": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
     "msp_pair_annotate": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int32, _P, C.c_int32,
                                     _P, _P, _P, _P, _P, C.POINTER(MspCamera), _P, _P]),
+    "msp_project_points": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "msp_annotate_points": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P, _P, _P,
                                       C.POINTER(MspCamera), _P, _P, _P, _P, _P, _P]),
     "msp_check_visibility": (C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(MspCamera), C.c_int32, _P, _P]),

@@ -93,16 +93,42 @@ __device__ __forceinline__ double row_dot4(const double* __restrict__ r, double 
   return __fma_rn(r[3], d, __fma_rn(r[2], c, __fma_rn(r[1], b, __dmul_rn(r[0], a))));
 }
 
+// The same products when NumPy multiplies a 4x4 by a SINGLE column ((4,4)@(4,1), as every per-point call of the
+// reference does: get_point_2d_coordinates_in_image, info_handler.py:291-305 -> IH:331,60,66).  That shape takes a
+// different BLAS path whose 4-term dot product is (a0 b0 + a2 b2) + (a1 b1 + a3 b3) with individually rounded products
+// and no FMA (verified bit-for-bit, 0 mismatches in 1 200 random dot products; tests/test_oracle_golden.py).
+__device__ __forceinline__ double dot4_single(double a0, double b0, double a1, double b1, double a2, double b2, double a3,
+                                              double b3) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a2, b2)), __dadd_rn(__dmul_rn(a1, b1), __dmul_rn(a3, b3)));
+}
+__device__ __forceinline__ double row_dot_h_single(const double* __restrict__ r, double x, double y, double z) {
+  return dot4_single(r[0], x, r[1], y, r[2], z, r[3], 1.0);
+}
+
 struct Proj {
   double u, v, z;
 };
 
 // Exact projection of one point.  STD = the w2c bottom row is [0,0,0,1] and K is [fx 0 cx 0; 0 fy cy 0; 0 0 1 0],
 // for which the zero terms of the BLAS dot products vanish exactly and cam.w == 1.
-template <bool STD>
+// SINGLE selects the one-column order above (per-point calls) instead of the N >= 2 gemm order (batch calls).
+template <bool STD, bool SINGLE = false>
 __device__ __forceinline__ Proj project_exact(const double* __restrict__ w /*16 or 12*/, const Intrinsics& K, double x,
                                               double y, double z) {
   Proj p;
+  if (SINGLE) {
+    const double X = row_dot_h_single(w + 0, x, y, z);
+    const double Y = row_dot_h_single(w + 4, x, y, z);
+    const double Z = row_dot_h_single(w + 8, x, y, z);
+    const double W = row_dot_h_single(w + 12, x, y, z);
+    p.z = Z;
+    const double i0 = dot4_single(K.k[0], X, K.k[1], Y, K.k[2], Z, K.k[3], W);
+    const double i1 = dot4_single(K.k[4], X, K.k[5], Y, K.k[6], Z, K.k[7], W);
+    const double i2 = dot4_single(K.k[8], X, K.k[9], Y, K.k[10], Z, K.k[11], W);
+    p.u = __ddiv_rn(i0, i2);
+    p.v = __ddiv_rn(i1, i2);
+    return p;
+  }
   const double X = row_dot_h(w + 0, x, y, z);
   const double Y = row_dot_h(w + 4, x, y, z);
   const double Z = row_dot_h(w + 8, x, y, z);
@@ -142,11 +168,11 @@ __device__ __forceinline__ bool depth_test(double z, uint16_t raw, const ImageGe
   return (z > 0.0) & (z < d);
 }
 
-template <bool STD>
+template <bool STD, bool SINGLE = false>
 __device__ __forceinline__ bool visible_exact(const double* __restrict__ w, const Intrinsics& K, const ImageGeom& g,
                                               const uint16_t* __restrict__ depth, double x, double y, double z,
                                               Proj& out) {
-  out = project_exact<STD>(w, K, x, y, z);
+  out = project_exact<STD, SINGLE>(w, K, x, y, z);
   bool vis = false;
   if (in_image(out, g) && out.z > 0.0) {
     vis = depth_test(out.z, ldg_u16_nc(depth + depth_index(out, g)), g);

@@ -331,7 +331,9 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(const PairParams p) {
         const bool fstd = KSTD && (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
         Proj pr;
         const uint16_t* dm = p.depth + (int64_t)f * p.depth_stride;
-        vis = fstd ? visible_exact<true>(w, p.K, p.g, dm, x, y, z, pr) : visible_exact<false>(w, p.K, p.g, dm, x, y, z, pr);
+        // per-point call of the reference (IH:291-305): one-column matmul order
+        (void)fstd;
+        vis = visible_exact<false, true>(w, p.K, p.g, dm, x, y, z, pr);
         pmx = permille(pr.u, p.g.img_w);
         pmy = permille(pr.v, p.g.img_h);
         dmm = depth_mm(pr.z);
@@ -386,24 +388,30 @@ struct AnnotParams {
   int32_t* depth_mm;
   int32_t* pix;
   uint8_t* visible;
+  int batch_order;  // 1: N >= 2 gemm order (batch projection of one frame), 0: single-point order (IH:291-305)
 };
 
 template <int DT, bool KSTD>
 __global__ void k_annotate(const AnnotParams p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.M) return;
-  const int32_t pt = p.point_ids[i], f = p.frame_ids[i];
+  const int64_t pt = p.point_ids ? (int64_t)p.point_ids[i] : i;
+  const int32_t f = p.frame_ids ? p.frame_ids[i] : 0;
   double x, y, z;
   PtTraits<DT>::load(p.pts, pt, x, y, z);
   const double* w = p.w2c + (int64_t)f * 16;
   const bool fstd = KSTD && (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
   Proj pr;
   bool vis;
-  if (p.depth != nullptr) {
-    const uint16_t* dm = p.depth + (int64_t)f * p.depth_stride;
-    vis = fstd ? visible_exact<true>(w, p.K, p.g, dm, x, y, z, pr) : visible_exact<false>(w, p.K, p.g, dm, x, y, z, pr);
-  } else {
+  if (p.batch_order) {
     pr = fstd ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
+    vis = in_image(pr, p.g) && pr.z > 0.0;
+    if (vis && p.depth != nullptr)
+      vis = depth_test(pr.z, ldg_u16_nc(p.depth + (int64_t)f * p.depth_stride + depth_index(pr, p.g)), p.g);
+  } else if (p.depth != nullptr) {
+    vis = visible_exact<false, true>(w, p.K, p.g, p.depth + (int64_t)f * p.depth_stride, x, y, z, pr);
+  } else {
+    pr = project_exact<false, true>(w, p.K, x, y, z);
     vis = in_image(pr, p.g) && pr.z > 0.0;
   }
   if (p.uvz) p.uvz[3 * i] = pr.u, p.uvz[3 * i + 1] = pr.v, p.uvz[3 * i + 2] = pr.z;
@@ -846,6 +854,35 @@ extern "C" int msp_pair_annotate(const uint32_t* mask_bits, int64_t n, int64_t m
   }
 #undef MSP_PAIR
   return check_launch("msp_pair_annotate");
+}
+
+extern "C" int msp_project_points(const void* pts, int64_t n, int32_t pts_dtype, const double* K16, const double* w2c_one,
+                                  double* uvz, void* stream) {
+  REQUIRE(n >= 0, "negative size");
+  REQUIRE(pts_dtype >= 0 && pts_dtype <= 2, "pts_dtype must be 0, 1 or 2");
+  if (n == 0) return MSP_OK;
+  REQUIRE(pts && K16 && w2c_one && uvz, "msp_project_points: NULL pointer");
+  REQUIRE(aligned16(pts), "pts must be 16-byte aligned");
+  AnnotParams p{};
+  msp_camera cam{1, 1, 1, 1, 1.0};
+  if (int rc = make_geom(&cam, &p.g)) return rc;
+  p.pts = pts, p.n = n, p.point_ids = nullptr, p.frame_ids = nullptr, p.M = n, p.w2c = w2c_one, p.depth = nullptr;
+  p.K = make_intr(K16);
+  p.uvz = uvz;
+  p.batch_order = (n >= 2) ? 1 : 0;   // NumPy multiplies a single column differently (see msp_device.cuh)
+  const bool ks = k_is_std(K16);
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+#define MSP_PRJ(DT)                                        \
+  if (ks) k_annotate<DT, true><<<grid, 128, 0, s>>>(p);   \
+  else k_annotate<DT, false><<<grid, 128, 0, s>>>(p)
+  switch (pts_dtype) {
+    case 0: MSP_PRJ(0); break;
+    case 1: MSP_PRJ(1); break;
+    default: MSP_PRJ(2); break;
+  }
+#undef MSP_PRJ
+  return check_launch("msp_project_points");
 }
 
 extern "C" int msp_annotate_points(const void* pts, int64_t n, int32_t pts_dtype, const int32_t* point_ids,

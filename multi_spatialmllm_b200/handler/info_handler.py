@@ -6,7 +6,7 @@ Same public names, argument order and return types, so the refe
 
 instead of the reference import.  The geometry methods run on the GPU through libmsp.so:
 
-    project_points                    <- IH:46-72     msp_pose_prepare + msp_annotate_points (float64, reference op order)
+    project_points                    <- IH:46-72     msp_pose_prepare + msp_project_points (float64, NumPy's op order for the shape)
     project_3d_point_to_image         <- IH:313-335
     check_point_in_image_boundary     <- IH:337-344   msp_check_visibility(mode=1)
     check_point_visibility_by_depth   <- IH:346-373   msp_check_visibility(mode=2)
@@ -62,14 +62,10 @@ def _project_on_device(points_xyz: np.ndarray, K: np.ndarray, E_c2w: np.ndarray)
         # np.linalg.inv raises LinAlgError on a singular pose and propagates NaN for non-finite ones (IH:57)
         if np.all(np.isfinite(E_c2w)):
             raise np.linalg.LinAlgError("Singular matrix")
-    ids = torch.arange(n, dtype=torch.int32, device=dev)
-    fr = torch.zeros((n,), dtype=torch.int32, device=dev)
     uvz = torch.empty((n, 3), dtype=torch.float64, device=dev)
     Kh = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(16))
-    cam = MspCamera(1, 1, 1, 1, 1.0)      # image geometry is irrelevant for a pure projection
-    check(lib.msp_annotate_points(pts.data_ptr(), n, _lib.MSP_PTS_F64X3, ids.data_ptr(), fr.data_ptr(), n,
-                                  Kh.ctypes.data, w2c.data_ptr(), None, C.byref(cam), uvz.data_ptr(), None, None, None,
-                                  None, _stream()), "msp_annotate_points")
+    check(lib.msp_project_points(pts.data_ptr(), n, _lib.MSP_PTS_F64X3, Kh.ctypes.data, w2c.data_ptr(), uvz.data_ptr(),
+                                 _stream()), "msp_project_points")
     out = uvz.cpu().numpy()
     return out[:, :2], out[:, 2].copy()
 

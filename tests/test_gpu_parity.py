@@ -79,7 +79,8 @@ def test_golden_point_annotation(golden_scannet):
     spot = g["ref_spot"]
     fr = [rows[int(k)] for k in spot[:, 0]]
     a = sc.annotate_points(spot[:, 1].astype(np.int32), fr)
-    np.testing.assert_allclose(a["uvz"].cpu().numpy(), spot[:, 2:5], rtol=RTOL)
+    # per-point calls: bit-identical floats (single-column matmul order + LAPACK-order inverse)
+    np.testing.assert_array_equal(a["uvz"].cpu().numpy(), spot[:, 2:5])
     np.testing.assert_array_equal(a["permille"].cpu().numpy(), spot[:, 5:7].astype(np.int32))
     np.testing.assert_array_equal(a["depth_mm"].cpu().numpy(), spot[:, 7].astype(np.int32))
     np.testing.assert_array_equal(a["pix"].cpu().numpy(), spot[:, 8:10].astype(np.int32))

@@ -87,8 +87,8 @@ def test_handler_geometry_matches_reference(disk_scene, golden_scannet):
     for k, image_id in enumerate(h.get_all_extrinsic_valid_image_ids(sid)):
         xy, z = h.project_3d_point_to_image(sid, image_id, pts)
         assert xy.dtype == np.float64 and xy.shape == (len(pts), 2) and z.shape == (len(pts),)
-        np.testing.assert_allclose(xy, g["ref_xy"][k], rtol=1e-9, atol=1e-7)
-        np.testing.assert_allclose(z, g["ref_z"][k], rtol=1e-9, atol=1e-9)
+        np.testing.assert_array_equal(xy, g["ref_xy"][k])          # bit-identical to the reference's floats
+        np.testing.assert_array_equal(z, g["ref_z"][k])
         # the two-step API on the REFERENCE's own xy/z must reproduce its masks bit for bit
         m = h.check_point_visibility(sid, image_id, g["ref_xy"][k], g["ref_z"][k])
         assert m.dtype == bool
@@ -103,12 +103,12 @@ def test_handler_geometry_matches_reference(disk_scene, golden_scannet):
         xy, z = h.get_point_2d_coordinates_in_image(sid, valid[int(row[0])], int(row[1]), align=True,
                                                     check_visible=True, return_depth=True)
         assert len(xy) == 1
-        np.testing.assert_allclose([xy[0][0], xy[0][1], z[0]], row[2:5], rtol=1e-9)
+        np.testing.assert_array_equal([xy[0][0], xy[0][1], z[0]], row[2:5])      # single-point call: exact as well
         assert [round((xy[0][0] / 1296) * 1000), round((xy[0][1] / 968) * 1000), round(z[0] * 1000)] == [int(v) for v in row[5:8]]
     # module-level project_points
     from multi_spatialmllm_b200.handler.info_handler import project_points
     xy, z = project_points(og.homogenize(pts[:100]), g["K"], g["ref_E_aligned"][0])
-    np.testing.assert_allclose(xy, g["ref_xy"][0][:100], rtol=1e-9, atol=1e-7)
+    np.testing.assert_array_equal(xy, g["ref_xy"][0][:100])
     with pytest.raises(ValueError):
         project_points(np.ones((3, 4)) * 2.0, g["K"], g["ref_E_aligned"][0])
 
