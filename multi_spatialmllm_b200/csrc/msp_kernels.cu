@@ -555,7 +555,8 @@ __global__ void __launch_bounds__(128) k_track_project(const float* __restrict__
     const double x = tracks[3 * i], y = tracks[3 * i + 1], z = tracks[3 * i + 2];
     if (world) {  // single_object_movement_engine_coord.py:446-451
 #pragma unroll
-      for (int r = 0; r < 3; ++r) world[3 * i + r] = row_dot4(s_c2w + 4 * r, x, y, z, 1.0);
+      // np.einsum('nij,nkj->nki') accumulates these 4-term products as (a0b0 + a2b2) + (a1b1 + a3b3), no FMA
+      for (int r = 0; r < 3; ++r) world[3 * i + r] = row_dot_h_single(s_c2w + 4 * r, x, y, z);
     }
     // single_object_movement_engine_coord.py:293-315 (float64 throughout, as under the pinned numpy 1.26)
     const double zg = __dadd_rn(z, 1e-8);
@@ -612,7 +613,9 @@ __global__ void k_track_pair_displacement(const double* __restrict__ world, cons
   inverse4(m2, c2);
   const double ex = c2[3] - c1[3], ey = c2[7] - c1[7], ez = c2[11] - c1[11];
   out[5 * i + 0] = sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx))));
-  for (int r = 0; r < 3; ++r) out[5 * i + 1 + r] = row_dot4(w1 + 4 * r, dx, dy, dz, 0.0);
+  // w2c[f1] @ [d, 0] is a (4,4)@(4,) product: same pairwise order as the single-column case
+  for (int r = 0; r < 3; ++r)
+    out[5 * i + 1 + r] = dot4_single(w1[4 * r], dx, w1[4 * r + 1], dy, w1[4 * r + 2], dz, w1[4 * r + 3], 0.0);
   out[5 * i + 4] = sqrt(__fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
 }
 
