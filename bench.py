@@ -357,7 +357,7 @@ def main_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args), "roofline": roofline,
+        "dtype": "f32/f64", "data": "synthetic", "config": workload_config(args), "roofline": roofline,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
     }
     line["config"]["scenes_resident_per_gpu"] = len(scenes)
