@@ -54,8 +54,12 @@ def test_two_rank_gloo_gather(tmp_path):
         dist.destroy_process_group()
     """))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    import socket
+    with socket.socket() as sock:                       # a free port, so parallel test runs do not collide
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     man = json.load(open(tmp_path / "manifest.json"))
