@@ -198,7 +198,7 @@ def main_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -420,8 +420,17 @@ def main_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=args.out, flush=True)
     return 0
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print to fd 1 (NCCL's version banner, torchrun notices) are
+    sent to stderr instead.  Returns a file object bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -439,6 +448,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    args.out = _claim_stdout()
     if args.impl == "reference":
         return main_reference(args)
     return main_gpu(args)
