@@ -254,7 +254,8 @@ def main_gpu(args):
     for i, n in enumerate(sizes):
         s = synth.make_scene(seed=rank * 100003 + i, n_points=n, n_frames=F, n_objects=12)
         sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids,
-                         num_objects=s.num_objects, image_hw=s.image_hw, depth_hw=s.depth_hw, device=dev)
+                         num_objects=s.num_objects, image_hw=s.image_hw, depth_hw=s.depth_hw, device=dev,
+                         reorder=args.reorder)
         sc.render_depth(margin_mm=1)
         sc.c2w_in, sc.A_in = sc.c2w, torch.from_numpy(s.axis_align.reshape(16)).to(dev)
         sc.pairs = torch.arange(F, dtype=torch.int32, device=dev).view(P, 2)
@@ -445,6 +446,7 @@ def main():
     ap.add_argument("--e2e-scenes", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs-per-worker", type=int, default=24)
+    ap.add_argument("--reorder", default=None, choices=[None, "morton"], help="store scene points in Morton order (tuning)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -419,3 +419,41 @@ def test_pose_prologue_is_bit_identical_to_numpy_fixture():
     E, w, _ = prep(g["mats"][:n], g["axis_align"])
     np.testing.assert_array_equal(E, g["aligned"])
     np.testing.assert_array_equal(w, g["aligned_inv"])
+
+
+def test_morton_reorder_is_transparent():
+    """reorder="morton": same masks (after un-permutation), counts, extents, annotations; pair records refer to the
+    caller's point numbering."""
+    import torch
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=31, n_points=60_001, n_frames=20, n_objects=7, shuffle_points=True)
+    kw = dict(axis_align=s.axis_align, instance_ids=s.instance_ids, num_objects=7)
+    a = DeviceScene(s.points, s.K, s.c2w, **kw)
+    b = DeviceScene(s.points, s.K, s.c2w, reorder="morton", **kw)
+    depth = a.render_depth(1)
+    b.set_depth(depth)
+    np.testing.assert_array_equal(b.render_zbuffer().cpu().numpy(), a.render_zbuffer().cpu().numpy())
+    _, ca = a.project_visibility_objects()
+    _, cb = b.project_visibility_objects()
+    ma, mb = a.mask_bool(), b.mask_bool()
+    np.testing.assert_array_equal(mb, ma)
+    np.testing.assert_array_equal(cb.cpu().numpy(), ca.cpu().numpy())
+    np.testing.assert_array_equal(b.object_extents().cpu().numpy(), a.object_extents().cpu().numpy())
+    vis = np.argwhere(ma)[::997]
+    ra = a.annotate_points(vis[:, 1], vis[:, 0])
+    rb = b.annotate_points(vis[:, 1], vis[:, 0])
+    for k in ra:
+        np.testing.assert_array_equal(rb[k].cpu().numpy(), ra[k].cpu().numpy())
+    pairs = np.array([(i, j) for i in range(20) for j in range(i + 1, 20)], np.int32)
+    sel = torch.randint(-2**31, 2**31 - 1, (len(pairs),), dtype=torch.int32)
+    rec = b.records_to_numpy(b.pair_annotate(pairs, sel, 1))
+    ref = a.records_to_numpy(a.pair_annotate(pairs, sel, 1))
+    np.testing.assert_array_equal(rec["inter"], ref["inter"])
+    np.testing.assert_array_equal(rec["uni"], ref["uni"])
+    has = rec["point_id"] >= 0
+    np.testing.assert_array_equal(has, ref["point_id"] >= 0)
+    assert ma[pairs[has, 0], rec["point_id"][has]].all() and ma[pairs[has, 1], rec["point_id"][has]].all()
+    assert (rec["flags"][has] == 3).all()
+    with pytest.raises(ValueError):
+        b.pair_annotate(pairs, np.zeros(len(pairs), np.uint32), 0)
