@@ -23,6 +23,7 @@
 #ifndef MSP_H_
 #define MSP_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -186,6 +187,45 @@ MSP_API int msp_track_cumulative_loss(const float* tracks, int32_t T, int32_t N,
  * camera-1 axes (w2c[f1] @ [d,0]) and the camera baseline ||c2-c1||.  out (M,5): dist, dx, dy, dz, cam_dist. */
 MSP_API int msp_track_pair_displacement(const double* world, const double* w2c, int32_t T, int32_t N, const int32_t* triples,
                                 int64_t M, double* out, void* stream);
+
+/* ---- dot annotation (the `*_dot` streams) --------------------------------------------------------------------------
+ * DE-dot:171, DC-dot:337-341, VC-dot:363,390-391, OM-dot:337: `cv2.circle(img, (x, y), r, color, -1)` and
+ * `cv2.putText(img, letter, org, FONT_HERSHEY_SIMPLEX, 1.0, color, 2)` on BGR uint8 images.  A mark is one circle
+ * (radius < 0: none; radius > MSP_MAX_MARK_RADIUS: skipped) plus one optional glyph (glyph < 0: none) painted in
+ * `bgr`.  Marks of one image MUST be contiguous in the array and are painted in array order (later marks overwrite
+ * earlier ones, as sequential cv2 calls do); marks of different images are independent.
+ * The circle is OpenCV's integer midpoint rasterisation, pixel-exact including clipping at the borders.  Glyphs are
+ * 1-bit masks, 32 rows of one uint32 each (bit c of row r = pixel (r, c)), with meta (off_x, off_y, width, height)
+ * giving the mask's top-left corner relative to the putText origin — multi_spatialmllm_b200/data/ holds the atlas
+ * rendered by cv2 for A-Z0-9.  Pixel-exact with cv2.putText whenever the glyph box lies inside the image; a glyph cut
+ * by the border is clipped per pixel (cv2 re-runs its line clipper there and moves a few edge pixels). */
+#define MSP_MAX_MARK_RADIUS 1024
+typedef struct msp_mark {
+  int32_t image;        /* index into the (B,H,W,3) batch; out of range: mark ignored */
+  int32_t x, y;         /* circle centre in pixels: int(u), int(v) */
+  int32_t radius;
+  int32_t glyph;        /* row of the atlas */
+  int32_t org_x, org_y; /* putText origin (bottom-left of the text) */
+  uint8_t bgr[3];
+  uint8_t reserved;
+} msp_mark;             /* 32 bytes */
+
+MSP_API int msp_draw_marks(uint8_t* images, int32_t B, int32_t H, int32_t W, const msp_mark* marks, int64_t M,
+                           const uint32_t* glyph_rows /* (G,32) or NULL */, const int32_t* glyph_meta /* (G,4) or NULL */,
+                           int32_t G, void* stream);
+
+/* JPEG glue for the same streams (cv2.imread / cv2.imwrite of DE-dot:221-229, DC-dot:333-346, VC-dot:357-397), over
+ * nvJPEG, which is dlopen'ed on first use (the call fails with MSP_EINVAL when libnvjpeg.so.12 is absent; nothing else
+ * in the library depends on it).  Streams are HOST buffers, images are device (H,W,3) BGR uint8.
+ * decode: enqueued on `stream` (the output is valid after the stream reaches that point).
+ * encode: 4:2:0, baseline Huffman; `host_out == NULL` only reports the size in *length; otherwise the call returns
+ * after the bitstream is in host_out (it synchronises `stream`).  Encoded bytes are nvJPEG's, not libjpeg's: the
+ * files differ from cv2.imwrite's in bytes, not in what they show. */
+MSP_API int msp_jpeg_info(const uint8_t* host_jpeg, size_t length, int32_t* height, int32_t* width);
+MSP_API int msp_jpeg_decode_bgr(const uint8_t* host_jpeg, size_t length, uint8_t* image_out, int32_t H, int32_t W,
+                                void* stream);
+MSP_API int msp_jpeg_encode_bgr(const uint8_t* image, int32_t H, int32_t W, int32_t quality, uint8_t* host_out,
+                                size_t capacity, size_t* length, void* stream);
 
 #ifdef __cplusplus
 }

@@ -620,6 +620,65 @@ __global__ void k_track_pair_displacement(const double* __restrict__ world, cons
 }
 
 // ================================================================================================
+// dot annotation: filled circles (OpenCV's midpoint walk) + glyph masks, one CTA per image's run of marks
+// ================================================================================================
+static_assert(sizeof(msp_mark) == 32, "msp_mark layout");
+
+__global__ void __launch_bounds__(256) k_draw_marks(uint8_t* __restrict__ images, int B, int H, int W,
+                                                    const msp_mark* __restrict__ marks, int64_t M,
+                                                    const uint32_t* __restrict__ glyph_rows,
+                                                    const int32_t* __restrict__ glyph_meta, int G) {
+  const int64_t head = blockIdx.x;
+  const int img = marks[head].image;
+  if (head > 0 && marks[head - 1].image == img) return;      // only the first mark of a run paints the run, in order
+  if (img < 0 || img >= B) return;
+  __shared__ int s_hw[MSP_MAX_MARK_RADIUS + 1];               // half-width of the span on rows y +- k
+  uint8_t* base = images + (int64_t)img * H * W * 3;
+  for (int64_t j = head; j < M && marks[j].image == img; ++j) {
+    const msp_mark m = marks[j];
+    const int r = m.radius;
+    if (r >= 0 && r <= MSP_MAX_MARK_RADIUS) {
+      if (threadIdx.x == 0) {
+        // cv::Circle (fill): (dx, dy) walks from (r, 0) while dx >= dy; rows +-dy get +-dx, rows +-dx get +-dy
+        int err = 0, dx = r, dy = 0, plus = 1, minus = (r << 1) - 1;
+        while (dx >= dy) {
+          s_hw[dy] = dx;                                      // dx only shrinks: the first visit of row dy is the widest
+          if (dx != dy) s_hw[dx] = dy;                        // dy only grows: the last visit of row dx wins
+          ++dy;
+          err += plus;
+          plus += 2;
+          if (err > 0) { err -= minus; --dx; minus -= 2; }
+        }
+      }
+      __syncthreads();
+      const int side = 2 * r + 1;
+      for (int t = threadIdx.x; t < side * side; t += blockDim.x) {
+        const int ky = t / side - r, kx = t % side - r;
+        if (abs(kx) > s_hw[abs(ky)]) continue;
+        const int px = m.x + kx, py = m.y + ky;
+        if (px < 0 || px >= W || py < 0 || py >= H) continue;
+        uint8_t* q = base + ((int64_t)py * W + px) * 3;
+        q[0] = m.bgr[0], q[1] = m.bgr[1], q[2] = m.bgr[2];
+      }
+      __syncthreads();
+    }
+    if (m.glyph >= 0 && m.glyph < G) {
+      const int ox = glyph_meta[4 * m.glyph], oy = glyph_meta[4 * m.glyph + 1];
+      const int gw = glyph_meta[4 * m.glyph + 2], gh = glyph_meta[4 * m.glyph + 3];
+      for (int t = threadIdx.x; t < 32 * 32; t += blockDim.x) {
+        const int row = t >> 5, col = t & 31;
+        if (row >= gh || col >= gw || !((glyph_rows[32 * m.glyph + row] >> col) & 1u)) continue;
+        const int px = m.org_x + ox + col, py = m.org_y + oy + row;
+        if (px < 0 || px >= W || py < 0 || py >= H) continue;
+        uint8_t* q = base + ((int64_t)py * W + px) * 3;
+        q[0] = m.bgr[0], q[1] = m.bgr[1], q[2] = m.bgr[2];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ================================================================================================
 // C ABI
 // ================================================================================================
 static bool k_is_std(const double* K) {
@@ -998,3 +1057,16 @@ extern "C" int msp_track_pair_displacement(const double* world, const double* w2
                                                                                           M, out);
   return check_launch("msp_track_pair_displacement");
 }
+
+extern "C" int msp_draw_marks(uint8_t* images, int32_t B, int32_t H, int32_t W, const msp_mark* marks, int64_t M,
+                              const uint32_t* glyph_rows, const int32_t* glyph_meta, int32_t G, void* stream) {
+  REQUIRE(B >= 0 && H >= 0 && W >= 0 && M >= 0 && G >= 0, "negative size");
+  if (M == 0 || B == 0 || H == 0 || W == 0) return MSP_OK;
+  REQUIRE(images && marks, "msp_draw_marks: NULL pointer");
+  REQUIRE(G == 0 || (glyph_rows && glyph_meta), "msp_draw_marks: glyph atlas missing");
+  REQUIRE(M < (1ll << 31), "too many marks");
+  k_draw_marks<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(images, B, H, W, marks, M, glyph_rows, glyph_meta, G);
+  return check_launch("msp_draw_marks");
+}
+
+#include "msp_jpeg.inl"

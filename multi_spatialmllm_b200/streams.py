@@ -47,6 +47,14 @@ class Templates:
         "visual_correspondence": {"task": ["Image-1: <image>\nImage-2: <image>\nCoordinates [ x , y ] are per-mille of width and height."],
                                   "questions": ["Where is the point [ {x1} , {y1} ] of Image-1 in Image-2?"],
                                   "answers": ["[ {x2} , {y2} ]"]},
+        "depth_estimation_dot": {"task": ["<image>\nA point is marked with a dot."],
+                                 "questions": ["What is the depth in mm of the marked point?"], "answers": ["`{depth}`"]},
+        "depth_comparison_dot": {"task": ["<image>\nTwo points are marked A and B."],
+                                 "closer_questions": ["Which marked point is closer to the camera?"],
+                                 "farther_questions": ["Which marked point is farther from the camera?"],
+                                 "closer_answers": ["{correct_label}"], "farther_answers": ["{correct_label}"]},
+        "visual_correspondence_dot": {"task": ["Image-1: <image>\nImage-2: <image>\nA point is marked in Image-1; candidates are lettered in Image-2."],
+                                      "questions": ["Which candidate is the marked point?"], "answers": ["{correct_label}"]},
         "camera_movement": {"task": ["Image-1: <image>\nImage-2: <image>\nDescribe the camera motion from Image-1 to Image-2."],
                             "questions": {q: [f"Report {q} of the second camera relative to the first."] for q in CAMERA_QUESTION_TYPES},
                             "answers": {q: ["`{" + q + "}`"] for q in CAMERA_QUESTION_TYPES}},
@@ -161,6 +169,141 @@ def visual_correspondence_samples(sc, scene_id, image_ids, pairs, sel, sel_mode=
                     "question_type": "visual_correspondence_coor_2_coor", "p1_list": [(x1, y1)], "p2_list": [(x2, y2)],
                     "gt_value": [x2, y2]})
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# `*_dot` variants: same geometry, plus the marks `annotate.draw_marks` paints on the colour frames
+# ------------------------------------------------------------------------------------------------
+DOT_RADIUS = 10                                            # DE-dot:171, DC-dot:337, VC-dot:363,390
+
+
+def _mark(marks, image, xy, color, letter=None, org=None, atlas=None, radius=DOT_RADIUS):
+    marks.append((image, int(xy[0]), int(xy[1]), radius, -1 if letter is None else atlas.index(letter),
+                  0 if org is None else int(org[0]), 0 if org is None else int(org[1]), tuple(int(c) for c in color), 0))
+
+
+def _finish_marks(marks):
+    from .annotate import MARK_DTYPE
+    return np.array(marks, dtype=MARK_DTYPE) if marks else np.zeros(0, MARK_DTYPE)
+
+
+def depth_estimation_dot_samples(sc, scene_id, image_ids, frames, points, templates=None, rng=None):
+    """DE-dot:197-262.  Returns (samples, marks, plan): output image k of the batch is a copy of colour frame
+    ``plan[k]`` with ``marks[marks["image"] == k]`` painted on it and is stored under ``samples[k]["image"][0]``."""
+    from .annotate import distinct_colors
+    tp, rng = (templates or Templates()).t["depth_estimation_dot"], rng or np.random.default_rng(0)
+    H, W = sc.image_hw
+    a = annotate(sc, frames, points)
+    out, marks, plan = [], [], []
+    for i, (f, p) in enumerate(zip(frames, points)):
+        if not a["visible"][i]:
+            continue
+        x, y = (int(v) for v in a["permille"][i])
+        depth, (u, v) = int(a["depth_mm"][i]), (int(c) for c in a["pix"][i])
+        image_id = image_ids[f]
+        _mark(marks, len(plan), (u, v), distinct_colors(1, rng)[0])
+        plan.append(int(f))
+        ans = _pick(rng, tp["answers"]).format(x1=x, y1=y, depth=depth)
+        out.append({"id": f"{scene_id}_{image_id}_point{int(p)}", "image": [f"{scene_id}/{image_id}_p{int(p)}_annotated.jpg"],
+                    "conversations": _conversation(_pick(rng, tp["task"]), _pick(rng, tp["questions"]), ans),
+                    "height_list": [H], "width_list": [W], "question_type": "depth_estimation_dot",
+                    "gt_value": depth, "ori_coordinates": [u, v]})
+    return out, _finish_marks(marks), plan
+
+
+def depth_comparison_dot_samples(sc, scene_id, image_ids, frames, point_pairs, closer_question, templates=None, rng=None,
+                                 atlas=None):
+    """DC-dot:262-373: letters A/B dealt at random, a random colour per point, label at (x+15, y+15), gt = letter."""
+    from .annotate import default_atlas
+    tp, rng = (templates or Templates()).t["depth_comparison_dot"], rng or np.random.default_rng(0)
+    atlas = atlas or default_atlas()
+    H, W = sc.image_hw
+    pp = np.asarray(point_pairs, np.int32).reshape(-1, 2)
+    a = annotate(sc, np.repeat(np.asarray(frames, np.int32), 2), pp.reshape(-1))
+    out, marks, plan = [], [], []
+    for i, f in enumerate(frames):
+        info = []
+        for s in range(2):
+            k = 2 * i + s
+            if a["visible"][k]:
+                info.append({"x": int(a["permille"][k][0]), "y": int(a["permille"][k][1]), "depth": int(a["depth_mm"][k]),
+                             "coords": (int(a["pix"][k][0]), int(a["pix"][k][1]))})
+        if len(info) != 2 or info[0]["depth"] == info[1]["depth"]:
+            continue
+        letters = ["A", "B"] if rng.random() < 0.5 else ["B", "A"]
+        if rng.random() < 0.5:
+            info = info[::-1]
+        for pi, letter in zip(info, letters):
+            pi["letter"] = letter
+        p1, p2 = info
+        closer, farther = (p1, p2) if p1["depth"] <= p2["depth"] else (p2, p1)
+        is_closer = bool(closer_question[i])
+        pick = closer if is_closer else farther
+        kind = "closer" if is_closer else "farther"
+        for pi in info:
+            cx, cy = pi["coords"]
+            _mark(marks, len(plan), (cx, cy), rng.integers(0, 256, 3), pi["letter"], (cx + 15, cy + 15), atlas)
+        plan.append(int(f))
+        image_id = image_ids[f]
+        stem = f"{image_id}_p{int(pp[i][0])}_p{int(pp[i][1])}"
+        out.append({"id": f"{scene_id}_{stem}", "image": [f"{scene_id}/{stem}_annotated.jpg"],
+                    "conversations": _conversation(_pick(rng, tp["task"]), _pick(rng, tp[f"{kind}_questions"]),
+                                                   _pick(rng, tp[f"{kind}_answers"]).format(correct_label=pick["letter"])),
+                    "height_list": [H], "width_list": [W], "question_type": "depth_comparison_annotated",
+                    "gt_value": pick["letter"], "points_info": info, "is_closer_question": is_closer})
+    return out, _finish_marks(marks), plan
+
+
+def visual_correspondence_dot_samples(sc, scene_id, image_ids, pairs, sel, sel_mode=1, start_idx=0, templates=None, rng=None,
+                                      atlas=None):
+    """VC-dot:357-426: the point dotted in image 1; in image 2 the true location and three random decoys
+    (x in [0, W-10], y in [0, H-10], != the true pixel), shuffled, lettered A-D at random, distinct colours,
+    labels at (x+15, y).  Two output images per sample (plan holds both frames)."""
+    from .annotate import default_atlas, distinct_colors
+    tp, rng = (templates or Templates()).t["visual_correspondence_dot"], rng or np.random.default_rng(0)
+    atlas = atlas or default_atlas()
+    H, W = sc.image_hw
+    rec = sc.records_to_numpy(sc.pair_annotate(np.asarray(pairs, np.int32), sel, sel_mode))
+    out, marks, plan = [], [], []
+    for i, ((fa, fb), r) in enumerate(zip(np.asarray(pairs).tolist(), rec)):
+        if r["point_id"] < 0 or r["flags"] != 3:
+            continue
+        u1, v1, u2, v2 = (int(c) for c in r["pix"])
+        correct = (u2, v2)
+        decoys = []
+        while len(decoys) < 3:
+            cand = (int(rng.integers(0, W - 10 + 1)), int(rng.integers(0, H - 10 + 1)))
+            if cand != correct:
+                decoys.append(cand)
+        pts = [correct] + decoys
+        order = rng.permutation(4)
+        labels = [("A", "B", "C", "D")[k] for k in rng.permutation(4)]
+        placed = [(labels[k], pts[order[k]]) for k in range(4)]
+        correct_label = next(lab for lab, pt in placed if pt == correct)
+        colors = distinct_colors(4, rng)
+        _mark(marks, len(plan), (u1, v1), rng.integers(0, 256, 3))
+        plan.append(int(fa))
+        for (lab, (x, y)), col in zip(placed, colors):
+            _mark(marks, len(plan), (x, y), col, lab, (x + 15, y), atlas)
+        plan.append(int(fb))
+        idx, pt, i1, i2 = start_idx + i, int(r["point_id"]), image_ids[fa], image_ids[fb]
+        out.append({"id": f"{idx}_p{pt}",
+                    "image": [f"{scene_id}/{idx}_point{pt}_{i1}_{i2}_img1.jpg", f"{scene_id}/{idx}_point{pt}_{i1}_{i2}_img2.jpg"],
+                    "conversations": _conversation(_pick(rng, tp["task"]), _pick(rng, tp["questions"]),
+                                                   _pick(rng, tp["answers"]).format(correct_label=correct_label)),
+                    "height_list": [H, H], "width_list": [W, W], "question_type": "visual_correspondence_multiple_choice",
+                    "gt_value": correct_label, "p1_list": [u1, v1], "p2_list": [correct] + decoys})
+    return out, _finish_marks(marks), plan
+
+
+def render_annotated(frames_bgr, plan, marks, device="cuda:0", atlas=None):
+    """Gather ``frames_bgr[plan]`` ((F,H,W,3) uint8, host or device) into a device batch and paint the marks."""
+    import torch
+    from .annotate import draw_marks
+    src = frames_bgr if isinstance(frames_bgr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames_bgr))
+    idx = torch.as_tensor(np.asarray(plan, np.int64))
+    batch = src.to(device)[idx.to(device)].contiguous() if src.is_cuda or src.numel() < (1 << 28) else src[idx].to(device)
+    return draw_marks(batch, marks, atlas)
 
 
 def camera_answer_values(rel_disp, yaw_angle, pitch_angle):

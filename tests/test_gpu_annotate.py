@@ -1,0 +1,161 @@
+"""Dot annotation through the C ABI (msp_draw_marks) against the cv2 golden and the restated raster; `*_dot` writers."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_paint(base, marks, atlas):
+    from oracle import drawing
+    out = base.copy()
+    for m in marks:
+        if 0 <= m["radius"]:
+            drawing.draw_filled_circle(out[m["image"]], int(m["x"]), int(m["y"]), int(m["radius"]), m["bgr"])
+        if m["glyph"] >= 0:
+            mask, off = atlas.mask(atlas.chars[m["glyph"]])
+            drawing.stamp_glyph(out[m["image"]], mask, off, (int(m["org_x"]), int(m["org_y"])), m["bgr"])
+    return out
+
+
+def test_draw_marks_matches_cv2_golden():
+    import torch
+    from multi_spatialmllm_b200.annotate import MARK_DTYPE, draw_marks
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "drawing_small.npz"))
+    marks = d["marks"].reshape(-1).view(MARK_DTYPE)
+    got = draw_marks(torch.from_numpy(d["base"]).cuda(), marks).cpu().numpy()
+    np.testing.assert_array_equal(got, d["expected"])
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_draw_marks_random_vs_oracle(seed):
+    """Every radius 0..40 (+ a large one), centres and labels inside, across and outside the borders, overlapping marks
+    painted in order, images without marks, marks without circle or without glyph."""
+    import torch
+    from multi_spatialmllm_b200.annotate import default_atlas, draw_marks, make_marks
+    rng = np.random.default_rng(100 + seed)
+    atlas = default_atlas()
+    B, H, W = 9, 70 + 13 * seed, 90 + 7 * seed
+    base = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    per_image = rng.integers(0, 14, B)
+    per_image[3] = 0
+    marks = make_marks(int(per_image.sum()))
+    marks["image"] = np.repeat(np.arange(B), per_image)
+    n = len(marks)
+    marks["radius"] = rng.choice(np.r_[-1, np.arange(41), 150], n)
+    marks["x"] = rng.integers(-45, W + 45, n)
+    marks["y"] = rng.integers(-45, H + 45, n)
+    marks["glyph"] = rng.integers(-1, len(atlas.chars), n)
+    marks["org_x"] = rng.integers(-40, W + 10, n)
+    marks["org_y"] = rng.integers(-10, H + 40, n)
+    marks["bgr"] = rng.integers(0, 256, (n, 3))
+    got = draw_marks(torch.from_numpy(base).cuda(), marks).cpu().numpy()
+    np.testing.assert_array_equal(got, _oracle_paint(base, marks, atlas))
+    np.testing.assert_array_equal(got[3], base[3])
+
+
+def test_draw_marks_rejects_bad_input():
+    import torch
+    from multi_spatialmllm_b200.annotate import draw_marks, make_marks
+    img = torch.zeros((2, 8, 8, 3), dtype=torch.uint8, device="cuda")
+    m = make_marks(3)
+    m["image"] = [0, 1, 0]                                        # runs of one image must be contiguous
+    with pytest.raises(ValueError):
+        draw_marks(img, m)
+    with pytest.raises(ValueError):
+        draw_marks(img.float(), make_marks(1))
+    assert draw_marks(img, make_marks(0)) is img
+
+
+def test_dot_stream_writers():
+    """`*_dot` samples carry the same integers as the `coor` writers; the marks painted on the frames are the
+    reference's (dot at int(u), int(v), radius 10; labels offset (15,15) / (15,0)); letters and gt agree."""
+    import torch
+    from multi_spatialmllm_b200 import streams, synth
+    from multi_spatialmllm_b200.annotate import default_atlas
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=3, n_points=30_000, n_frames=8, n_objects=4)
+    sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align)
+    sc.render_depth(1)
+    sc.project_visibility()
+    mb = sc.mask_bool()
+    rng = np.random.default_rng(0)
+    frames = [f for f in range(8) if mb[f].sum() >= 2]
+    pts = [int(rng.choice(np.flatnonzero(mb[f]))) for f in frames]
+    H, W = sc.image_hw
+    colour = np.broadcast_to((np.arange(W, dtype=np.uint8)[None, :, None] + np.arange(8, dtype=np.uint8)[:, None, None, None]),
+                             (8, H, W, 3)).copy()
+    atlas = default_atlas()
+
+    de, marks, plan = streams.depth_estimation_dot_samples(sc, s.scene_id, s.image_ids, frames, pts, rng=np.random.default_rng(1))
+    ref = streams.depth_estimation_samples(sc, s.scene_id, s.image_ids, frames, pts, variant="dot", rng=np.random.default_rng(1))
+    assert len(de) == len(ref) == len(plan) == len(marks) > 0
+    for a, b, m in zip(de, ref, marks):
+        assert a["id"] == b["id"] and a["gt_value"] == b["gt_value"] and a["ori_coordinates"] == b["ori_coordinates"]
+        assert a["image"] == b["image"] and a["question_type"] == "depth_estimation_dot"
+        assert [int(m["x"]), int(m["y"])] == a["ori_coordinates"] and m["radius"] == 10 and m["glyph"] == -1
+    got = streams.render_annotated(colour, plan, marks).cpu().numpy()
+    np.testing.assert_array_equal(got, _oracle_paint(colour[plan], marks, atlas))
+
+    pairs_pts = [rng.choice(np.flatnonzero(mb[f]), 2, replace=False).tolist() for f in frames]
+    closer = rng.random(len(frames)) < 0.5
+    dc, marks, plan = streams.depth_comparison_dot_samples(sc, s.scene_id, s.image_ids, frames, pairs_pts, closer,
+                                                           rng=np.random.default_rng(2))
+    assert len(dc) == len(plan) and len(marks) == 2 * len(dc) > 0
+    for k, smp in enumerate(dc):
+        info = smp["points_info"]
+        assert sorted(p["letter"] for p in info) == ["A", "B"] and smp["question_type"] == "depth_comparison_annotated"
+        want = min(info, key=lambda p: p["depth"]) if smp["is_closer_question"] else max(info, key=lambda p: p["depth"])
+        assert smp["gt_value"] == want["letter"]
+        for p, m in zip(info, marks[2 * k:2 * k + 2]):
+            assert (int(m["x"]), int(m["y"])) == tuple(p["coords"]) and atlas.chars[m["glyph"]] == p["letter"]
+            assert (int(m["org_x"]), int(m["org_y"])) == (p["coords"][0] + 15, p["coords"][1] + 15)
+    got = streams.render_annotated(torch.from_numpy(colour).cuda(), plan, marks).cpu().numpy()
+    np.testing.assert_array_equal(got, _oracle_paint(colour[plan], marks, atlas))
+
+    pairs = np.array([(i, j) for i in range(8) for j in range(8) if i != j], np.int32)[::4]
+    sel = torch.from_numpy(rng.integers(0, 2**31, len(pairs)).astype(np.int32))
+    vc, marks, plan = streams.visual_correspondence_dot_samples(sc, s.scene_id, s.image_ids, pairs, sel, 1, start_idx=7,
+                                                                rng=np.random.default_rng(3))
+    coor = streams.visual_correspondence_samples(sc, s.scene_id, s.image_ids, pairs, sel, 1, start_idx=7)
+    assert len(vc) == len(coor) > 0 and len(plan) == 2 * len(vc) and len(marks) == 5 * len(vc)
+    for k, smp in enumerate(vc):
+        m1, m2 = marks[5 * k], marks[5 * k + 1:5 * k + 5]
+        assert [int(m1["x"]), int(m1["y"])] == smp["p1_list"] and m1["glyph"] == -1
+        assert len(set(smp["p2_list"])) == 4 and sorted(atlas.chars[g] for g in m2["glyph"]) == ["A", "B", "C", "D"]
+        hit = [atlas.chars[m["glyph"]] for m in m2 if (int(m["x"]), int(m["y"])) == tuple(smp["p2_list"][0])]
+        assert hit == [smp["gt_value"]]
+        assert all((int(m["org_x"]), int(m["org_y"])) == (int(m["x"]) + 15, int(m["y"])) for m in m2)
+        assert smp["id"].startswith(f"{7 + [tuple(p) for p in pairs.tolist()].index((plan[2 * k], plan[2 * k + 1]))}_p")
+    got = streams.render_annotated(colour, plan, marks).cpu().numpy()
+    np.testing.assert_array_equal(got, _oracle_paint(colour[plan], marks, atlas))
+
+
+def test_jpeg_roundtrip_through_nvjpeg():
+    """Decode -> paint -> encode stays on the device.  JPEG is lossy and nvJPEG's DCT is not libjpeg's, so the bar is a
+    tolerance (stated here): decode within 3 grey levels mean / 99 % of pixels within 8 of cv2's decode of the same
+    stream; encode at quality 95 >= 35 dB PSNR after cv2 decodes it."""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from multi_spatialmllm_b200.annotate import draw_marks, jpeg_decode, jpeg_encode, make_marks
+    H, W = 968, 1296
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([(xx // 5) % 256, (yy // 3) % 256, ((xx + yy) // 7) % 256], -1).astype(np.uint8)
+    ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 95])
+    assert ok
+    want = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+    got = jpeg_decode(enc.tobytes())
+    assert tuple(got.shape) == (H, W, 3)
+    diff = np.abs(got.cpu().numpy().astype(np.int32) - want.astype(np.int32))
+    assert diff.mean() < 3.0 and (diff <= 8).mean() > 0.99, (diff.mean(), (diff <= 8).mean())
+    m = make_marks(1)
+    m["x"], m["y"], m["radius"], m["bgr"] = 600, 400, 10, (0, 0, 255)
+    painted = draw_marks(got[None].contiguous(), m)[0]
+    back = cv2.imdecode(np.frombuffer(jpeg_encode(painted, 95), np.uint8), cv2.IMREAD_COLOR)
+    ref = painted.cpu().numpy().astype(np.float64)
+    psnr = 10 * np.log10(255.0 ** 2 / np.mean((back.astype(np.float64) - ref) ** 2))
+    assert back.shape == (H, W, 3) and psnr >= 35.0, psnr
+    assert tuple(back[400, 600]) [2] > 200 and back[400, 600][0] < 60          # the red dot survived
+    with pytest.raises(Exception):
+        jpeg_decode(b"not a jpeg")

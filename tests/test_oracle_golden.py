@@ -1,5 +1,6 @@
 """The oracle (oracle/geometry.py) against the reference's own outputs (tests/golden/*.npz,
 made by tests/golden/make_golden.py from the unmodified reference)."""
+import os
 import numpy as np
 import pytest
 
@@ -160,3 +161,52 @@ def test_single_column_matmul_order_is_pairwise():
         import pytest
         pytest.skip(f"this machine's BLAS uses other orders ({same_single}/{total} single, {same_chain}/{total} chain); "
                     "the device mirrors the build container's OpenBLAS 0.3.30 SkylakeX kernels")
+
+
+# ---- dot annotation raster (oracle/drawing.py) ---------------------------------------------------------------------
+def _draw_golden():
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "drawing_small.npz"))
+    from multi_spatialmllm_b200.annotate import MARK_DTYPE
+    return d["base"], d["expected"], d["marks"].reshape(-1).view(MARK_DTYPE)
+
+
+def _oracle_paint(base, marks, atlas):
+    from oracle import drawing
+    out = base.copy()
+    for m in marks:
+        drawing.draw_filled_circle(out[m["image"]], int(m["x"]), int(m["y"]), int(m["radius"]), m["bgr"])
+        if m["glyph"] >= 0:
+            mask, off = atlas.mask(atlas.chars[m["glyph"]])
+            drawing.stamp_glyph(out[m["image"]], mask, off, (int(m["org_x"]), int(m["org_y"])), m["bgr"])
+    return out
+
+
+def test_drawing_oracle_matches_cv2_golden():
+    """The restated midpoint circle + glyph stamping reproduce images painted by cv2 (tests/golden/make_golden_draw.py)."""
+    from multi_spatialmllm_b200.annotate import GlyphAtlas
+    base, expected, marks = _draw_golden()
+    np.testing.assert_array_equal(_oracle_paint(base, marks, GlyphAtlas()), expected)
+
+
+def test_drawing_oracle_matches_cv2_live():
+    """When cv2 is importable: every radius 0..40 at random (also clipped) centres, and the shipped atlas against putText."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import drawing
+    from multi_spatialmllm_b200.annotate import GlyphAtlas
+    rng = np.random.default_rng(5)
+    for r in range(41):
+        for _ in range(8):
+            H, W = (int(v) for v in rng.integers(20, 120, 2))
+            x, y = int(rng.integers(-r - 3, W + r + 3)), int(rng.integers(-r - 3, H + r + 3))
+            a = np.zeros((H, W, 3), np.uint8)
+            b = a.copy()
+            cv2.circle(a, (x, y), r, (9, 200, 31), -1)
+            drawing.draw_filled_circle(b, x, y, r, (9, 200, 31))
+            np.testing.assert_array_equal(a, b)
+    atlas = GlyphAtlas()
+    for ch in atlas.chars:
+        a = np.zeros((64, 64, 3), np.uint8)
+        b = a.copy()
+        cv2.putText(a, ch, (20, 45), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (1, 2, 3), 2)
+        drawing.stamp_glyph(b, *atlas.mask(ch), (20, 45), (1, 2, 3))
+        np.testing.assert_array_equal(a, b)
