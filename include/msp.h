@@ -36,7 +36,7 @@ extern "C" {
 #define MSP_API
 #endif
 
-#define MSP_VERSION 100
+#define MSP_VERSION 101
 
 #define MSP_OK 0
 #define MSP_EINVAL (-1)   /* bad argument (null pointer, size, alignment, dtype) */
@@ -187,6 +187,29 @@ MSP_API int msp_track_cumulative_loss(const float* tracks, int32_t T, int32_t N,
  * camera-1 axes (w2c[f1] @ [d,0]) and the camera baseline ||c2-c1||.  out (M,5): dist, dx, dy, dz, cam_dist. */
 MSP_API int msp_track_pair_displacement(const double* world, const double* w2c, int32_t T, int32_t N, const int32_t* triples,
                                 int64_t M, double* out, void* stream);
+
+/* ---- visibility table text (the reference's canonical parquet, make_visibility_info.py:59-65) --------------------------
+ * The "values" column — json.dumps of every frame's sorted visible point ids (image_to_points, MVI:103-104) and of every
+ * point's sorted frame ids (point_to_images, MVI:107-118) — written byte-exactly from the bit masks, so that the host
+ * never builds a Python list.  Two phases per table: *_size fills bytes-per-row, the caller makes the exclusive scan
+ * (offsets[0] = 0 ... offsets[rows] = total) and allocates `text`, *_write places row i at text + offsets[i].
+ * Empty rows are "[]"; separators are ", " (json.dumps defaults).
+ *  frame_rows (R) int32: mask rows to emit, in output order (NULL = 0..R-1).  For image_to_points pass the valid frames
+ *  in image_ids order (dict insertion order, MVI:93-104); for point_to_images pass them sorted by id string (MVI:116-118).
+ *  ids (R, id_pitch) uint8 + id_len (R) uint8: the frame id strings in frame_rows order; they must consist of characters
+ *  json.dumps leaves unescaped (printable ASCII except '"' and '\\'). */
+MSP_API int msp_visibility_json_points_size(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                            const int32_t* frame_rows, int32_t R, int64_t* row_bytes, void* stream);
+MSP_API int msp_visibility_json_points_write(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                             const int32_t* frame_rows, int32_t R, const int64_t* offsets /* (R+1) */,
+                                             uint8_t* text, void* stream);
+MSP_API int msp_visibility_json_images_size(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                            const int32_t* frame_rows, int32_t R, const uint8_t* id_len,
+                                            int64_t* point_bytes /* (n) */, void* stream);
+MSP_API int msp_visibility_json_images_write(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                             const int32_t* frame_rows, int32_t R, const uint8_t* ids, int32_t id_pitch,
+                                             const uint8_t* id_len, const int64_t* offsets /* (n+1) */, uint8_t* text,
+                                             void* stream);
 
 /* ---- dot annotation (the `*_dot` streams) --------------------------------------------------------------------------
  * DE-dot:171, DC-dot:337-341, VC-dot:363,390-391, OM-dot:337: `cv2.circle(img, (x, y), r, color, -1)` and

@@ -60,6 +60,10 @@ _SIGNATURES = {
     "msp_jpeg_info": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "msp_jpeg_decode_bgr": (C.c_int, [_P, C.c_size_t, _P, C.c_int32, C.c_int32, _P]),
     "msp_jpeg_encode_bgr": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),
+    "msp_visibility_json_points_size": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P]),
+    "msp_visibility_json_points_write": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P]),
+    "msp_visibility_json_images_size": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P]),
+    "msp_visibility_json_images_write": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P]),
     "msp_draw_marks": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, C.c_int32, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -10,6 +10,7 @@
 #include "msp.h"
 #include "msp_device.cuh"
 #include "msp_cull.cuh"
+#include "msp_tables.cuh"
 
 using namespace msp;
 
@@ -1067,6 +1068,58 @@ extern "C" int msp_draw_marks(uint8_t* images, int32_t B, int32_t H, int32_t W, 
   REQUIRE(M < (1ll << 31), "too many marks");
   k_draw_marks<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(images, B, H, W, marks, M, glyph_rows, glyph_meta, G);
   return check_launch("msp_draw_marks");
+}
+
+// ---- visibility table text (msp_tables.cuh)
+static int json_common_checks(const uint32_t* mask_bits, int64_t n, int64_t stride, int32_t R) {
+  REQUIRE(n >= 0 && R >= 0, "negative size");
+  REQUIRE(n < (1ll << 31), "point ids must fit int32");
+  REQUIRE(mask_bits != nullptr || n == 0 || R == 0, "mask_bits is NULL");
+  REQUIRE(stride >= (n + 31) / 32, "mask_stride_words too small");
+  return MSP_OK;
+}
+
+extern "C" int msp_visibility_json_points_size(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                               const int32_t* frame_rows, int32_t R, int64_t* row_bytes, void* stream) {
+  if (int rc = json_common_checks(mask_bits, n, mask_stride_words, R)) return rc;
+  if (R == 0) return MSP_OK;
+  REQUIRE(row_bytes != nullptr, "msp_visibility_json_points_size: NULL pointer");
+  k_json_point_lists<false><<<(unsigned)R, kJsonThreads, 0, (cudaStream_t)stream>>>(mask_bits, n, mask_stride_words, frame_rows,
+                                                                                    nullptr, row_bytes, nullptr);
+  return check_launch("msp_visibility_json_points_size");
+}
+
+extern "C" int msp_visibility_json_points_write(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                                const int32_t* frame_rows, int32_t R, const int64_t* offsets, uint8_t* text,
+                                                void* stream) {
+  if (int rc = json_common_checks(mask_bits, n, mask_stride_words, R)) return rc;
+  if (R == 0) return MSP_OK;
+  REQUIRE(offsets && text, "msp_visibility_json_points_write: NULL pointer");
+  k_json_point_lists<true><<<(unsigned)R, kJsonThreads, 0, (cudaStream_t)stream>>>(mask_bits, n, mask_stride_words, frame_rows,
+                                                                                   offsets, nullptr, text);
+  return check_launch("msp_visibility_json_points_write");
+}
+
+extern "C" int msp_visibility_json_images_size(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                               const int32_t* frame_rows, int32_t R, const uint8_t* id_len,
+                                               int64_t* point_bytes, void* stream) {
+  if (int rc = json_common_checks(mask_bits, n, mask_stride_words, R)) return rc;
+  if (n == 0) return MSP_OK;
+  REQUIRE(point_bytes && (id_len || R == 0), "msp_visibility_json_images_size: NULL pointer");
+  k_json_image_lists<false><<<(unsigned)((n + kJsonThreads - 1) / kJsonThreads), kJsonThreads, 0, (cudaStream_t)stream>>>(
+      mask_bits, n, mask_stride_words, frame_rows, R, nullptr, 0, id_len, nullptr, point_bytes, nullptr);
+  return check_launch("msp_visibility_json_images_size");
+}
+
+extern "C" int msp_visibility_json_images_write(const uint32_t* mask_bits, int64_t n, int64_t mask_stride_words,
+                                                const int32_t* frame_rows, int32_t R, const uint8_t* ids, int32_t id_pitch,
+                                                const uint8_t* id_len, const int64_t* offsets, uint8_t* text, void* stream) {
+  if (int rc = json_common_checks(mask_bits, n, mask_stride_words, R)) return rc;
+  if (n == 0) return MSP_OK;
+  REQUIRE(offsets && text && ((ids && id_len && id_pitch > 0) || R == 0), "msp_visibility_json_images_write: NULL pointer");
+  k_json_image_lists<true><<<(unsigned)((n + kJsonThreads - 1) / kJsonThreads), kJsonThreads, 0, (cudaStream_t)stream>>>(
+      mask_bits, n, mask_stride_words, frame_rows, R, ids, id_pitch, id_len, offsets, nullptr, text);
+  return check_launch("msp_visibility_json_images_write");
 }
 
 #include "msp_jpeg.inl"

@@ -91,24 +91,172 @@ def device_scene_from_handler(scene_infos, scene_id: str, device="cuda:0"):
     return sc, image_ids
 
 
+# ------------------------------------------------------------------------------------------------
+# device-formatted tables: the JSON text / columns leave the GPU ready for Arrow, no Python lists on the way
+# ------------------------------------------------------------------------------------------------
+_JSON_SAFE = frozenset(chr(c) for c in range(0x20, 0x7f)) - {'"', "\\"}
+
+
+def _check_json_safe(ids):
+    for s in ids:
+        if not isinstance(s, str) or len(s) > 255 or not set(s) <= _JSON_SAFE:
+            raise ValueError(f"frame id {s!r} would be escaped by json.dumps (or is longer than 255 bytes): not supported "
+                             "by the device formatter")
+
+
+def visibility_arrow_table(sc: "engine.DeviceScene", scene_id: str, image_ids):
+    """The rows convert_pkl_to_parquet writes for one scene (MVI:59-65) as a pyarrow Table (key, values).
+
+    Row order and bytes are the reference's: one ``{scene}:image_to_points:{image_id}`` row per valid frame in
+    ``image_ids`` order (MVI:93-104), then one ``{scene}:point_to_images:{p}`` row per point (MVI:116-118, ids sorted as
+    strings).  The ``values`` text is written on the device from the bit masks (msp_visibility_json_*); the host only
+    wraps the returned buffers.
+    """
+    import ctypes as C  # noqa: F401
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import torch
+    from ._lib import check, lib
+    from .engine import _ptr, _stream
+    if sc.perm is not None:
+        raise ValueError("the table formatter needs the caller's point order (reorder=None)")
+    if sc.mask is None:
+        sc.project_visibility()
+    dev = sc.device
+    valid = sc.valid.cpu().numpy().astype(bool)
+    assert len(image_ids) == sc.F, "one id per frame row"
+    rows_a = np.flatnonzero(valid).astype(np.int32)
+    ids_a = [image_ids[f] for f in rows_a]
+    _check_json_safe(ids_a)
+    order = np.argsort(np.asarray(ids_a, dtype=object).astype(str), kind="stable") if len(ids_a) else np.empty(0, np.int64)
+    rows_b = rows_a[order]
+    ids_b = [ids_a[k] for k in order]
+    if any(ids_b[k] == ids_b[k + 1] for k in range(len(ids_b) - 1)):
+        raise ValueError("duplicate frame ids")                      # the reference's set() would merge them
+    R, n = int(len(rows_a)), sc.n
+    pitch = max([len(s) for s in ids_b], default=1) or 1
+    id_tab = np.zeros((max(R, 1), pitch), np.uint8)
+    id_len = np.zeros(max(R, 1), np.uint8)
+    for k, s_ in enumerate(ids_b):
+        b = s_.encode("ascii")
+        id_tab[k, :len(b)] = np.frombuffer(b, np.uint8)
+        id_len[k] = len(b)
+    rows_a_d = torch.from_numpy(rows_a).to(dev)
+    rows_b_d = torch.from_numpy(np.ascontiguousarray(rows_b)).to(dev)
+    id_tab_d, id_len_d = torch.from_numpy(id_tab).to(dev), torch.from_numpy(id_len).to(dev)
+    sizes = torch.empty(R + n, dtype=torch.int64, device=dev)
+    st = _stream()
+    check(lib.msp_visibility_json_points_size(_ptr(sc.mask), n, sc.stride, _ptr(rows_a_d), R, sizes.data_ptr(), st),
+          "msp_visibility_json_points_size")
+    check(lib.msp_visibility_json_images_size(_ptr(sc.mask), n, sc.stride, _ptr(rows_b_d), R, _ptr(id_len_d),
+                                              sizes[R:].data_ptr() if n else None, st), "msp_visibility_json_images_size")
+    offs = torch.zeros(R + n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(sizes, 0, out=offs[1:])
+    total = int(offs[-1].item())                                     # the one sync: the text buffer has to be sized
+    text = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    check(lib.msp_visibility_json_points_write(_ptr(sc.mask), n, sc.stride, _ptr(rows_a_d), R, offs.data_ptr(),
+                                               text.data_ptr(), st), "msp_visibility_json_points_write")
+    check(lib.msp_visibility_json_images_write(_ptr(sc.mask), n, sc.stride, _ptr(rows_b_d), R, _ptr(id_tab_d), pitch,
+                                               _ptr(id_len_d), offs[R:].data_ptr(), text.data_ptr(), st),
+          "msp_visibility_json_images_write")
+    small = total < 2**31
+    offs_h = (offs.to(torch.int32) if small else offs).cpu().numpy()
+    text_h = text[:total].cpu().numpy()
+    cls = pa.StringArray if small else pa.LargeStringArray
+    values = cls.from_buffers(R + n, pa.py_buffer(offs_h), pa.py_buffer(text_h))
+    str_t = pa.string() if small else pa.large_string()
+    key_a = pa.array([f"{scene_id}:image_to_points:{i}" for i in ids_a], type=str_t)
+    key_b = pc.binary_join_element_wise(pa.scalar(f"{scene_id}:point_to_images:", type=str_t),
+                                        pc.cast(pa.array(np.arange(n, dtype=np.int64)), str_t), pa.scalar("", type=str_t))
+    return pa.table({"key": pa.concat_arrays([key_a, key_b]), "values": values})
+
+
+def relations_arrow_table(sc: "engine.DeviceScene", scene_id: str, image_ids):
+    """calculate_frames_relations.process_scene + save_overlap_info (CFR:139-197, 28-57) for one scene as a pyarrow
+    Table with the reference's columns; every i<j pair of valid frames in itertools.combinations order, no Python loop."""
+    import pyarrow as pa
+    if sc.mask is None:
+        sc.project_visibility()
+    valid = np.flatnonzero(sc.valid.cpu().numpy())
+    ii, jj = np.triu_indices(len(valid), k=1)                        # == combinations(valid, 2) order
+    pairs = np.stack([valid[ii], valid[jj]], 1).astype(np.int32)
+    P = len(pairs)
+    if P:
+        rec = sc.records_to_numpy(sc.pair_annotate(pairs, np.zeros(P, np.uint32), sel_mode=0))
+    else:
+        rec = np.zeros(0, engine.PAIR_RECORD_DTYPE)
+    ids = pa.array([str(i) for i in image_ids], type=pa.string())
+    return pa.table({
+        "scene_id": pa.DictionaryArray.from_arrays(pa.array(np.zeros(P, np.int32)), pa.array([scene_id])).cast(pa.string()),
+        "image_id1": ids.take(pa.array(pairs[:, 0])) if P else pa.array([], pa.string()),
+        "image_id2": ids.take(pa.array(pairs[:, 1])) if P else pa.array([], pa.string()),
+        "overlap": pa.array(np.ascontiguousarray(rec["overlap"])), "distance": pa.array(np.ascontiguousarray(rec["distance"])),
+        "yaw": pa.array(np.ascontiguousarray(rec["dyaw"])), "pitch": pa.array(np.ascontiguousarray(rec["dpitch"])),
+    })
+
+
+class _ParquetStream:
+    """Row-group-per-scene parquet writer; the file is created by the first non-empty table (the reference writes no file
+    when there is nothing to save, CFR:52-54).  Writes run on one background thread so that Arrow's encoding/compression of
+    scene k overlaps the GPU work of scene k+1."""
+
+    def __init__(self, path: str):
+        from concurrent.futures import ThreadPoolExecutor
+        self.path, self.writer, self.rows = path, None, 0
+        self._pool, self._pending = ThreadPoolExecutor(1), None
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+
+    def _write(self, table):
+        import pyarrow.parquet as pq
+        if self.writer is None:
+            self.writer = pq.ParquetWriter(self.path, table.schema)
+        self.writer.write_table(table)
+
+    def write(self, table):
+        if table.num_rows == 0:
+            return
+        if self._pending is not None:
+            self._pending.result()
+        self.rows += table.num_rows
+        self._pending = self._pool.submit(self._write, table)
+
+    def close(self) -> int:
+        if self._pending is not None:
+            self._pending.result()
+        self._pool.shutdown()
+        if self.writer is not None:
+            self.writer.close()
+        return self.rows
+
+
 def run_visibility_split(scene_infos, output_file: str, scene_ids=None, device="cuda:0") -> dict:
-    """make_visibility_info.run_split (MVI:127-177) on the GPU; writes the canonical parquet."""
-    tables = {}
+    """make_visibility_info.run_split + convert_pkl_to_parquet (MVI:127-177, 38-73) on the GPU: streams one row group
+    per scene into the canonical parquet (same keys, same JSON text, same row order as the reference's file)."""
+    out = _ParquetStream(output_file)
+    n_scenes = 0
     for sid in (scene_ids if scene_ids is not None else scene_infos.get_all_scene_ids()):
         sc, image_ids = device_scene_from_handler(scene_infos, sid, device)
-        tables[sid] = engine.process_scene_visibility(sc, image_ids)
-    save_visibility_parquet(tables, output_file)
-    return tables
+        out.write(visibility_arrow_table(sc, sid, image_ids))
+        n_scenes += 1
+    return {"scenes": n_scenes, "rows": out.close(), "file": output_file}
 
 
 def run_relations_split(scene_infos, output_parquet: str, scene_ids=None, device="cuda:0") -> dict:
-    """calculate_frames_relations.run_split (CFR:200-253) on the GPU."""
-    info = {}
+    """calculate_frames_relations.run_split (CFR:200-253) on the GPU: <file> and <file>_nonzero.parquet (CFR:59-84;
+    NaN != 0.0, so pairs with an empty union stay in the nonzero table like in the reference)."""
+    import pyarrow.compute as pc
+    full = _ParquetStream(output_parquet)
+    nonzero = _ParquetStream(output_parquet.replace(".parquet", "_nonzero.parquet"))
+    n_scenes = 0
     for sid in (scene_ids if scene_ids is not None else scene_infos.get_all_scene_ids()):
         sc, image_ids = device_scene_from_handler(scene_infos, sid, device)
-        info[sid] = engine.process_scene_relations(sc, image_ids)
-    save_overlap_parquet(info, output_parquet)
-    return info
+        t = relations_arrow_table(sc, sid, image_ids)
+        full.write(t)
+        if t.num_rows:
+            ov = t["overlap"]
+            nonzero.write(t.filter(pc.or_(pc.is_nan(ov), pc.not_equal(ov, 0.0))))
+        n_scenes += 1
+    return {"scenes": n_scenes, "rows": full.close(), "rows_nonzero": nonzero.close(), "file": output_parquet}
 
 
 def object_visibility_scene(scene_infos, scene_id: str, sc: "engine.DeviceScene", image_ids) -> dict:

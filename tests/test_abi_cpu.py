@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(_lib.lib, name), f"{name} declared in msp.h but not exported by libmsp.so"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared          # the ctypes table covers the whole header
-    assert _lib.version() == 100
+    assert _lib.version() == 101
     assert _lib.lib.msp_last_error() is not None
 
 

@@ -184,3 +184,22 @@ def test_object_coverage_and_perception_stream(disk_scene, golden_scannet):
         o = int(x["id"].split("_")[2])
         assert x["gt_value"] == int(round(dims[o] * 1000)) and x["question_type"] == "object_perception_height_estimation"
         assert len(x["image"]) == len(x["height_list"]) == int(x["id"].split("_")[3]) and json.dumps(x)
+
+
+def test_parquet_stream_cpu(tmp_path):
+    """Row-group-per-scene writer: concatenation in write order, no file when nothing was written (CFR:52-54)."""
+    import pyarrow as pa
+    from multi_spatialmllm_b200 import tables
+    path = str(tmp_path / "sub" / "t.parquet")
+    w = tables._ParquetStream(path)
+    w.write(pa.table({"key": ["a", "b"], "values": ["[]", "[1, 2]"]}))
+    w.write(pa.table({"key": pa.array([], pa.string()), "values": pa.array([], pa.string())}))
+    w.write(pa.table({"key": ["c"], "values": ['["00000"]']}))
+    assert w.close() == 3
+    df = pd.read_parquet(path)
+    assert df["key"].tolist() == ["a", "b", "c"] and df["values"].tolist() == ["[]", "[1, 2]", '["00000"]']
+    empty = tables._ParquetStream(str(tmp_path / "none.parquet"))
+    assert empty.close() == 0 and not os.path.exists(str(tmp_path / "none.parquet"))
+    with pytest.raises(ValueError):
+        tables._check_json_safe(['quo"te'])
+    tables._check_json_safe(["00005", "frame_12", "a b"])
