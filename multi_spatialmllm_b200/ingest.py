@@ -1,0 +1,446 @@
+"""ScanNet ingestion: raw scans -> the on-disk layout the geometry path reads.
+
+Host-side I/O and format conversion only (no geometry of the hot path).  Mirrors three reference scripts under
+spatial_engine/utils/scannet_utils/ and writes byte-compatible outputs:
+
+  export / export_one_scan / batch_export   <- batch_load_scannet_data.py:28-313 (BLS) + scannet_utils.py (SU)
+        *_vh_clean_2.ply, *.aggregation.json, *_vh_clean_2.0.010000.segs.json, <scan>.txt, label tsv
+        -> unaligned_points.npy (N,6) f32, aligned_points.npy (N,6) f64, semantic/instance/raw_category masks,
+           per-object point clouds, scenes_train_val_info.pkl {scan: {obj: {aligned_bbox, unaligned_bbox, raw_category},
+           axis_align_matrix, num_objects}}
+  SensReader / extract_posed_images         <- extract_posed_images.py:28-177 (EPI)
+        <scan>.sens -> posed_images/<scan>/{%05d.jpg, %05d.png, %05d.txt, intrinsic.txt}
+  update_info_with_images                   <- update_info_file_with_images.py:13-72 (UIF)
+        -> scenes_*_info_i_D{k}.pkl with images_info / intrinsic_matrix / num_posed_images
+
+Differences from the reference, all on purpose: the .sens file is memory-mapped and frames are sliced lazily (the
+reference unpacks every byte through struct "c" and keeps all frames in RAM); vertex labelling is vectorised; the colour
+JPEG of a frame is written verbatim instead of being decoded and re-encoded (EPI:128-134 re-compresses every image at
+imageio's default quality, a second lossy pass) — pass ``reencode_color=True`` for a decode/encode round trip.
+Depth PNGs hold the same uint16 pixels; pose / intrinsic text files are character-identical ("%f" per value, EPI:137-142).
+"""
+from __future__ import annotations
+
+import csv
+import json
+import mmap
+import os
+import pickle
+import struct
+import zlib
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------------------
+# PLY (ScanNet meshes are binary_little_endian with x,y,z,red,green,blue,alpha vertices)
+# ------------------------------------------------------------------------------------------------
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2",
+              "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4",
+              "double": "f8", "float64": "f8"}
+
+
+def read_ply_vertices(path: str) -> np.ndarray:
+    """The ``vertex`` element of a PLY file as a structured array (what plyfile's ``plydata["vertex"].data`` holds)."""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt, elements = None, []
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: unterminated PLY header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] == "comment" or tok[0] == "obj_info":
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append((tok[1], int(tok[2]), []))
+            elif tok[0] == "property":
+                elements[-1][2].append(tok[1:])
+            elif tok[0] == "end_header":
+                break
+        if not elements or elements[0][0] != "vertex":
+            raise ValueError(f"{path}: the first PLY element must be 'vertex'")
+        _, count, props = elements[0]
+        if any(p[0] == "list" for p in props):
+            raise ValueError(f"{path}: list properties on vertices are not supported")
+        names = [p[1] for p in props]
+        if fmt == "ascii":
+            rows = np.loadtxt(f, max_rows=count, ndmin=2) if count else np.zeros((0, len(props)))
+            out = np.zeros(count, dtype=[(n, _PLY_TYPES[p[0]]) for n, p in zip(names, props)])
+            for k, n in enumerate(names):
+                out[n] = rows[:, k]
+            return out
+        if fmt not in ("binary_little_endian", "binary_big_endian"):
+            raise ValueError(f"{path}: unknown PLY format {fmt!r}")
+        order = "<" if fmt == "binary_little_endian" else ">"
+        dt = np.dtype([(n, order + _PLY_TYPES[p[0]]) for n, p in zip(names, props)])
+        data = np.frombuffer(f.read(count * dt.itemsize), dtype=dt, count=count)
+        return data
+
+
+def read_mesh_vertices_rgb(path: str) -> np.ndarray:
+    """scannet_utils.read_mesh_vertices_rgb (SU:146-165): (N,6) float32 x,y,z,red,green,blue (RGB in 0..255)."""
+    v = read_ply_vertices(path)
+    out = np.zeros((len(v), 6), np.float32)
+    for k, n in enumerate(("x", "y", "z", "red", "green", "blue")):
+        out[:, k] = v[n]
+    return out
+
+
+def read_label_mapping(filename: str, label_from="raw_category", label_to="nyu40id") -> dict:
+    """SU:118-127."""
+    mapping = {}
+    with open(filename) as f:
+        for row in csv.DictReader(f, delimiter="\t"):
+            mapping[row[label_from]] = int(row[label_to])
+    keys = list(mapping)
+    if keys:
+        try:
+            int(keys[0])
+            mapping = {int(k): v for k, v in mapping.items()}
+        except ValueError:
+            pass
+    return mapping
+
+
+def read_aggregation(filename: str):
+    """SU:17-35: ({object id (1-indexed): segments}, {label: segments of every object with that label})."""
+    with open(filename) as f:
+        groups = json.load(f)["segGroups"]
+    object_id_to_segs, label_to_segs = {}, {}
+    for g in groups:
+        object_id_to_segs[g["objectId"] + 1] = g["segments"]
+        if g["label"] in label_to_segs:
+            label_to_segs[g["label"]].extend(g["segments"])     # note: aliases the first object's list, like SU:30-33
+        else:
+            label_to_segs[g["label"]] = g["segments"]
+    return object_id_to_segs, label_to_segs
+
+
+def read_seg_indices(filename: str) -> np.ndarray:
+    """The per-vertex segment id array of SU:38-50 (the reference inverts it into a dict of vertex lists)."""
+    with open(filename) as f:
+        return np.asarray(json.load(f)["segIndices"], dtype=np.int64)
+
+
+def read_axis_alignment(meta_file: str) -> np.ndarray:
+    """BLS:55-65: the 16 numbers after ``axisAlignment =`` (identity when the line is absent, e.g. test scans)."""
+    with open(meta_file) as f:
+        for line in f:
+            if "axisAlignment" in line:
+                return np.array([float(x) for x in line.split("=", 1)[1].split()]).reshape(4, 4)
+    return np.eye(4)
+
+
+def extract_bbox(vertices: np.ndarray, object_ids, object_id_to_label_id: dict, instance_ids: np.ndarray):
+    """SU:53-101: per-object [centre, size, label] boxes and point clouds (None for objects without points)."""
+    num = len(np.unique(list(object_ids)))
+    boxes = np.zeros((num, 7))
+    clouds = [None] * num
+    for obj_id in object_ids:
+        sel = instance_ids == obj_id
+        pc = vertices[sel]
+        if len(pc) == 0:
+            print(f"WARNING: object id {obj_id} does not have points. Corresponding entry is set to None.")
+            continue
+        lo, hi = pc[:, :3].min(0), pc[:, :3].max(0)
+        boxes[obj_id - 1] = np.concatenate([(lo + hi) / 2.0, hi - lo, np.array([object_id_to_label_id[obj_id]])])
+        clouds[obj_id - 1] = pc
+    return boxes, clouds
+
+
+def export(mesh_file, agg_file, seg_file, meta_file, label_map_file, test_mode=False):
+    """batch_load_scannet_data.export (BLS:28-135): same 12-tuple, same dtypes."""
+    label_map = read_label_mapping(label_map_file)
+    mesh = read_mesh_vertices_rgb(mesh_file)
+    A = read_axis_alignment(meta_file)
+    pts = np.ones((mesh.shape[0], 4))
+    pts[:, :3] = mesh[:, :3]
+    pts = np.dot(pts, A.transpose())                                   # BLS:66-69 (float64)
+    aligned = np.concatenate([pts[:, :3], mesh[:, 3:]], axis=1)
+    if test_mode:
+        return (mesh, aligned, None, None, None, None, None, None, None, None, None, A)
+    object_id_to_segs, label_to_segs = read_aggregation(agg_file)
+    seg = read_seg_indices(seg_file)
+    n = len(seg)
+    present = np.zeros(int(seg.max()) + 1 if n else 1, bool)
+    present[seg] = True
+
+    def check(s):
+        if s < 0 or s >= len(present) or not present[s]:
+            raise KeyError(s)                                          # seg_to_verts[seg] in the reference
+
+    # vertex -> label / category: later (category, segment) assignments overwrite earlier ones (BLS:81-86)
+    seg_label = np.zeros(len(present), np.uint32)
+    seg_cat = np.full(len(present), -1, np.int64)
+    cats = list(label_to_segs)
+    for ci, cat in enumerate(cats):
+        for s in label_to_segs[cat]:
+            check(s)
+            seg_label[s] = label_map[cat]
+            seg_cat[s] = ci
+    label_ids = seg_label[seg] if n else np.zeros(0, np.uint32)
+    raw_categories = np.array([None] * n)
+    vc = seg_cat[seg] if n else np.zeros(0, np.int64)
+    for ci, cat in enumerate(cats):
+        raw_categories[vc == ci] = cat
+    # vertex -> instance (BLS:88-101); first vertex of the first listed segment names the object's label / category
+    seg_obj = np.zeros(len(present), np.uint32)
+    for obj, segs in object_id_to_segs.items():
+        for s in segs:
+            check(s)
+            seg_obj[s] = obj
+    instance_ids = seg_obj[seg] if n else np.zeros(0, np.uint32)
+    first_vertex = {}
+    if n:
+        order = np.argsort(seg, kind="stable")
+        uniq, start = np.unique(seg[order], return_index=True)
+        first_vertex = dict(zip(uniq.tolist(), order[start].tolist()))
+    obj_label, obj_cat = {}, {}
+    for obj, segs in object_id_to_segs.items():
+        if segs:
+            v0 = first_vertex[segs[0]]
+            obj_label[obj] = label_ids[v0]
+            obj_cat[obj] = raw_categories[v0]
+    ub, upc = extract_bbox(mesh, object_id_to_segs, obj_label, instance_ids)
+    ab, apc = extract_bbox(aligned, object_id_to_segs, obj_label, instance_ids)
+    return (mesh, aligned, label_ids, raw_categories, instance_ids, ub, ab, upc, apc, obj_cat, obj_label, A)
+
+
+def export_one_scan(scan_name, output_prefix, max_num_point, label_map_file, scannet_dir, test_mode=False) -> dict:
+    """BLS:138-249: writes the per-scene npy files and returns {scan_name: scene_info}."""
+    os.makedirs(output_prefix, exist_ok=True)
+    base = os.path.join(scannet_dir, scan_name, scan_name)
+    (mesh, aligned, sem, cats, inst, ub, ab, upc, apc, obj_cat, _obj_label, A) = export(
+        base + "_vh_clean_2.ply", base + ".aggregation.json", base + "_vh_clean_2.0.010000.segs.json", base + ".txt",
+        label_map_file, test_mode)
+    if max_num_point is not None and mesh.shape[0] > int(max_num_point):
+        choices = np.random.choice(mesh.shape[0], int(max_num_point), replace=False)      # BLS:188-197 (global RNG)
+        mesh = mesh[choices]
+        if not test_mode:
+            sem, inst, cats = sem[choices], inst[choices], cats[choices]
+    np.save(f"{output_prefix}/unaligned_points.npy", mesh)
+    np.save(f"{output_prefix}/aligned_points.npy", aligned)
+    info = {}
+    if not test_mode:
+        np.save(f"{output_prefix}/semantic_mask.npy", sem)
+        np.save(f"{output_prefix}/instance_mask.npy", inst)
+        np.save(f"{output_prefix}/raw_category_mask.npy", cats)
+        assert len(sem) == len(inst) == len(cats) == len(mesh), "mask / vertex lengths differ"
+        for obj_id, (abox, ubox) in enumerate(zip(ab, ub)):
+            name = obj_cat.get(obj_id + 1, "None")
+            if name == "None":
+                raise SystemExit(f"Something wrong for the raw category name of object {obj_id} in scan {scan_name}.")
+            info[obj_id] = {"aligned_bbox": abox, "unaligned_bbox": ubox, "raw_category": name}
+            np.save(f"{output_prefix}/object_{obj_id}_aligned_points.npy", apc[obj_id])
+            np.save(f"{output_prefix}/object_{obj_id}_unaligned_points.npy", upc[obj_id])
+        info["axis_align_matrix"] = A
+        info["num_objects"] = len(ab)
+    return {scan_name: info}
+
+
+def batch_export(max_num_point, output_folder, scan_names_file, label_map_file, scannet_dir, test_mode=False,
+                 num_workers=1) -> str | None:
+    """BLS:270-313: every scan of the list -> per-scene files + scenes_{train_val,test}_info.pkl."""
+    if test_mode and not os.path.exists(scannet_dir):
+        return None
+    os.makedirs(output_folder, exist_ok=True)
+    names = sorted(line.rstrip() for line in open(scan_names_file))
+    jobs = [(s, os.path.join(output_folder, s), max_num_point, label_map_file, scannet_dir, test_mode) for s in names]
+    if num_workers > 1:
+        from multiprocessing import Pool
+        with Pool(num_workers) as p:
+            results = p.starmap(export_one_scan, jobs)
+    else:
+        results = [export_one_scan(*j) for j in jobs]
+    all_info = {}
+    for r in results:
+        all_info.update(r)
+    out = os.path.join(output_folder, "scenes_test_info.pkl" if test_mode else "scenes_train_val_info.pkl")
+    with open(out, "wb") as f:
+        pickle.dump(all_info, f)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# .sens (extract_posed_images.py:28-177)
+# ------------------------------------------------------------------------------------------------
+COMPRESSION_TYPE_COLOR = {-1: "unknown", 0: "raw", 1: "png", 2: "jpeg"}
+COMPRESSION_TYPE_DEPTH = {-1: "unknown", 0: "raw_ushort", 1: "zlib_ushort", 2: "occi_ushort"}
+
+
+class SensFrame:
+    __slots__ = ("camera_to_world", "timestamp_color", "timestamp_depth", "_buf", "_color", "_depth")
+
+    def __init__(self, buf, pos):
+        self.camera_to_world = np.frombuffer(buf, "<f4", 16, pos).reshape(4, 4).copy()
+        self.timestamp_color, self.timestamp_depth, nc, nd = struct.unpack_from("<QQQQ", buf, pos + 64)
+        self._buf = buf
+        self._color = (pos + 96, nc)
+        self._depth = (pos + 96 + nc, nd)
+
+    @property
+    def end(self) -> int:
+        return self._depth[0] + self._depth[1]
+
+    @property
+    def color_data(self) -> memoryview:
+        return memoryview(self._buf)[self._color[0]:self._color[0] + self._color[1]]
+
+    @property
+    def depth_data(self) -> memoryview:
+        return memoryview(self._buf)[self._depth[0]:self._depth[0] + self._depth[1]]
+
+
+class SensReader:
+    """SensorData (EPI:59-111): header fields under the same names, ``frames`` = every ``frame_skip``-th frame."""
+
+    VERSION = 4
+
+    def __init__(self, filename: str, frame_skip: int = 1):
+        self._file = open(filename, "rb")
+        self._map = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_READ)
+        b, pos = self._map, 0
+        (version,) = struct.unpack_from("<I", b, pos)
+        assert version == self.VERSION, f"unsupported .sens version {version}"
+        (strlen,) = struct.unpack_from("<Q", b, 4)
+        pos = 12
+        self.sensor_name = bytes(b[pos:pos + strlen])
+        pos += strlen
+        mats = np.frombuffer(b, "<f4", 64, pos).reshape(4, 4, 4).copy()
+        self.intrinsic_color, self.extrinsic_color, self.intrinsic_depth, self.extrinsic_depth = mats
+        pos += 256
+        cc, dc, self.color_width, self.color_height, self.depth_width, self.depth_height = struct.unpack_from("<iiIIII", b, pos)
+        self.color_compression_type = COMPRESSION_TYPE_COLOR[cc]
+        self.depth_compression_type = COMPRESSION_TYPE_DEPTH[dc]
+        pos += 24
+        (self.depth_shift,) = struct.unpack_from("<f", b, pos)
+        (self.num_frames,) = struct.unpack_from("<Q", b, pos + 4)
+        pos += 12
+        self.frames = []
+        for i in range(self.num_frames):
+            fr = SensFrame(b, pos)
+            pos = fr.end
+            if i % frame_skip == 0:
+                self.frames.append(fr)
+        assert len(self.frames) == len(range(0, self.num_frames, frame_skip)), "Number of frames mismatch."
+
+    def close(self):
+        self.frames = []
+        try:
+            self._map.close()
+        except BufferError:          # a caller still holds a view of a frame
+            pass
+        self._file.close()
+
+    def depth_image(self, k: int) -> np.ndarray:
+        """EPI:50-52, 117-121: (depth_height, depth_width) uint16."""
+        assert self.depth_compression_type == "zlib_ushort"
+        raw = zlib.decompress(self.frames[k].depth_data)
+        return np.frombuffer(raw, dtype="<u2").reshape(self.depth_height, self.depth_width)
+
+    def depth_stack(self) -> np.ndarray:
+        """All exported frames as one (F, h, w) uint16 array — the layout DeviceScene / HostScene take."""
+        out = np.empty((len(self.frames), self.depth_height, self.depth_width), np.uint16)
+        for k in range(len(self.frames)):
+            out[k] = self.depth_image(k)
+        return out
+
+    def poses(self) -> np.ndarray:
+        """(F,4,4) float64 camera->world, rounded through the "%f" text form exactly like the exported pose files
+        (EPI:137-150 writes them, UIF:50-53 parses them back): what the geometry path actually consumes."""
+        return np.array([[[float("%f" % float(v)) for v in row] for row in fr.camera_to_world] for fr in self.frames]
+                        ).reshape(-1, 4, 4)
+
+
+def _mat_text(m) -> str:
+    """save_mat_to_file (EPI:137-142): np.savetxt(fmt="%f") of each row."""
+    return "".join(" ".join("%f" % float(v) for v in row) + "\n" for row in m)
+
+
+def extract_posed_images(sens_path: str, output_path: str, frame_skip: int = 1, reencode_color: bool = False,
+                         skip_existing: bool = True) -> int:
+    """process_scene (EPI:160-177): colour jpg, depth png, pose txt per exported frame + intrinsic.txt.
+    Returns the number of frames written (0 when ``output_path`` exists and ``skip_existing``, EPI:168-171)."""
+    import cv2
+    if skip_existing and os.path.exists(output_path):
+        print(f"{output_path} already exists. Skip.")
+        return 0
+    data = SensReader(sens_path, frame_skip)
+    os.makedirs(output_path, exist_ok=True)
+    assert data.color_compression_type == "jpeg"
+    for k, fr in enumerate(data.frames):
+        stem = os.path.join(output_path, str(k).zfill(5))
+        if reencode_color:
+            img = cv2.imdecode(np.frombuffer(fr.color_data, np.uint8), cv2.IMREAD_COLOR)
+            cv2.imwrite(stem + ".jpg", img)
+        else:
+            with open(stem + ".jpg", "wb") as f:
+                f.write(fr.color_data)
+        cv2.imwrite(stem + ".png", data.depth_image(k))
+        with open(stem + ".txt", "w") as f:
+            f.write(_mat_text(fr.camera_to_world))
+    with open(os.path.join(output_path, "intrinsic.txt"), "w") as f:
+        f.write(_mat_text(data.intrinsic_color))
+    n = len(data.frames)
+    data.close()
+    return n
+
+
+def _read_mat(path: str) -> np.ndarray:
+    with open(path) as f:
+        return np.array([list(map(float, line.split())) for line in f.readlines()])
+
+
+def update_info_with_images(scene_infos: dict, posed_images_dir: str, frame_skip: int = 5) -> dict:
+    """update_info_file_with_images.py:19-69: adds num_posed_images / images_info / intrinsic_matrix per scene (in
+    place, like the reference) from the extracted posed_images tree."""
+    for scene_id in scene_infos:
+        scene_path = os.path.join(posed_images_dir, scene_id)
+        jpgs = sorted(f for f in os.listdir(scene_path) if f.endswith(".jpg"))
+        image_data = {}
+        for i, filename in enumerate(jpgs):
+            if i % frame_skip:
+                continue
+            image_id = filename.split(".")[0]
+            image_data[image_id] = {
+                "image_path": f"posed_images/{scene_id}/{filename}",
+                "depth_image_path": f"posed_images/{scene_id}/{image_id}.png",
+                "extrinsic_matrix": _read_mat(os.path.join(scene_path, f"{image_id}.txt")),
+            }
+        scene_infos[scene_id].update({"num_posed_images": len(image_data), "images_info": image_data,
+                                      "intrinsic_matrix": _read_mat(os.path.join(scene_path, "intrinsic.txt"))})
+    return scene_infos
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description="ScanNet ingestion (batch_load_scannet_data / extract_posed_images / "
+                                             "update_info_file_with_images in one driver)")
+    ap.add_argument("--scannet_dir", default="scans")
+    ap.add_argument("--scan_names_file", default="data/scannet/meta_data/scannet_train.txt")
+    ap.add_argument("--label_map_file", default="data/scannet/meta_data/scannetv2-labels.combined.tsv")
+    ap.add_argument("--output_folder", default="data/scannet/scannet_instance_data")
+    ap.add_argument("--posed_images", default="data/scannet/posed_images")
+    ap.add_argument("--frame_skip", type=int, default=1, help="export every n-th .sens frame (EPI --frame_skip)")
+    ap.add_argument("--info_skip", type=int, default=5, help="keep every n-th exported image in the info file (UIF)")
+    ap.add_argument("--max_num_point", default=None)
+    ap.add_argument("--nproc", type=int, default=1)
+    a = ap.parse_args(argv)
+    pkl = batch_export(a.max_num_point, a.output_folder, a.scan_names_file, a.label_map_file, a.scannet_dir,
+                       num_workers=a.nproc)
+    with open(pkl, "rb") as f:
+        infos = pickle.load(f)
+    for scan in infos:
+        extract_posed_images(os.path.join(a.scannet_dir, scan, f"{scan}.sens"), os.path.join(a.posed_images, scan), a.frame_skip)
+    update_info_with_images(infos, a.posed_images, a.info_skip)
+    out = pkl.replace(".pkl", f"_i_D{a.info_skip}.pkl")
+    with open(out, "wb") as f:
+        pickle.dump(infos, f)
+    print(f"wrote {out}")
+
+
+if __name__ == "__main__":
+    main()
