@@ -188,6 +188,16 @@ MSP_API int msp_track_cumulative_loss(const float* tracks, int32_t T, int32_t N,
 MSP_API int msp_track_pair_displacement(const double* world, const double* w2c, int32_t T, int32_t N, const int32_t* triples,
                                 int64_t M, double* out, void* stream);
 
+/* OM-coord:484-498 for n_tracks selected tracks at once: the distances between ALL i<j pairs of each track's visible
+ * frames, in the reference's pair order (i-major) and in np.linalg.norm(axis=1)'s arithmetic ((dx*dx + dy*dy) + dz*dz).
+ *  world (T,N,3) float64 from msp_track_project; track_ids (n_tracks); vis_frames: the ascending visible frame indices
+ *  of every track back to back, frame_offsets (n_tracks+1) into it; pair_offsets (n_tracks+1) into dist, with
+ *  pair_offsets[t+1]-pair_offsets[t] = V_t(V_t-1)/2; max_pairs_per_track sizes the grid. */
+MSP_API int msp_track_all_pair_distances(const double* world, int32_t T, int32_t N, const int32_t* track_ids,
+                                         int32_t n_tracks, const int32_t* vis_frames, const int64_t* frame_offsets,
+                                         const int64_t* pair_offsets, int64_t max_pairs_per_track, double* dist,
+                                         void* stream);
+
 /* ---- visibility table text (the reference's canonical parquet, make_visibility_info.py:59-65) --------------------------
  * The "values" column — json.dumps of every frame's sorted visible point ids (image_to_points, MVI:103-104) and of every
  * point's sorted frame ids (point_to_images, MVI:107-118) — written byte-exactly from the bit masks, so that the host

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "msp_track_project": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "msp_track_cumulative_loss": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double, _P, _P]),
     "msp_track_pair_displacement": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P]),
+    "msp_track_all_pair_distances": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P]),
     "msp_jpeg_info": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "msp_jpeg_decode_bgr": (C.c_int, [_P, C.c_size_t, _P, C.c_int32, C.c_int32, _P]),
     "msp_jpeg_encode_bgr": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),

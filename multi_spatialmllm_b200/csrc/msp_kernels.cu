@@ -620,6 +620,35 @@ __global__ void k_track_pair_displacement(const double* __restrict__ world, cons
   out[5 * i + 4] = sqrt(__fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex))));
 }
 
+// All i<j pairs of each selected track's visible frames (single_object_movement_engine_coord.py:484-498): the reference
+// builds the pair list in a Python comprehension and calls np.linalg.norm(points2 - points1, axis=1), which sums the three
+// squares as (dx*dx + dy*dy) + dz*dz with individually rounded products (NumPy's add.reduce over the short axis; no FMA).
+// grid.y = track, grid.x covers that track's pairs; k -> (i, j) in lexicographic order.
+__global__ void __launch_bounds__(256) k_track_all_pair_distances(const double* __restrict__ world, int N,
+                                                                  const int32_t* __restrict__ track_ids,
+                                                                  const int32_t* __restrict__ vis_frames,
+                                                                  const int64_t* __restrict__ frame_offsets,
+                                                                  const int64_t* __restrict__ pair_offsets,
+                                                                  double* __restrict__ dist) {
+  const int t = blockIdx.y;
+  const int64_t fo = frame_offsets[t];
+  const int64_t V = frame_offsets[t + 1] - fo;
+  const int64_t P = V * (V - 1) / 2;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P) return;
+  int64_t i = (int64_t)((2.0 * V - 1.0 - sqrt((2.0 * V - 1.0) * (2.0 * V - 1.0) - 8.0 * (double)k)) * 0.5);
+  if (i < 0) i = 0;
+  if (i > V - 2) i = V - 2;
+  while (i * (2 * V - i - 1) / 2 > k) --i;
+  while ((i + 1) * (2 * V - i - 2) / 2 <= k) ++i;
+  const int64_t j = k - i * (2 * V - i - 1) / 2 + i + 1;
+  const int pt = track_ids[t];
+  const double* a = world + 3 * ((int64_t)vis_frames[fo + i] * N + pt);
+  const double* b = world + 3 * ((int64_t)vis_frames[fo + j] * N + pt);
+  const double dx = __dsub_rn(b[0], a[0]), dy = __dsub_rn(b[1], a[1]), dz = __dsub_rn(b[2], a[2]);
+  dist[pair_offsets[t] + k] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
 // ================================================================================================
 // dot annotation: filled circles (OpenCV's midpoint walk) + glyph masks, one CTA per image's run of marks
 // ================================================================================================
@@ -1057,6 +1086,21 @@ extern "C" int msp_track_pair_displacement(const double* world, const double* w2
   k_track_pair_displacement<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(world, w2c, T, N, triples,
                                                                                           M, out);
   return check_launch("msp_track_pair_displacement");
+}
+
+extern "C" int msp_track_all_pair_distances(const double* world, int32_t T, int32_t N, const int32_t* track_ids,
+                                            int32_t n_tracks, const int32_t* vis_frames, const int64_t* frame_offsets,
+                                            const int64_t* pair_offsets, int64_t max_pairs_per_track, double* dist,
+                                            void* stream) {
+  REQUIRE(T >= 0 && N >= 0 && n_tracks >= 0 && max_pairs_per_track >= 0, "negative size");
+  if (n_tracks == 0 || max_pairs_per_track == 0) return MSP_OK;
+  REQUIRE(world && track_ids && vis_frames && frame_offsets && pair_offsets && dist, "msp_track_all_pair_distances: NULL pointer");
+  REQUIRE(n_tracks <= 65535, "at most 65535 tracks per call");
+  REQUIRE(max_pairs_per_track < (1ll << 31) * 256, "too many pairs per track");
+  const dim3 grid((unsigned)((max_pairs_per_track + 255) / 256), (unsigned)n_tracks);
+  k_track_all_pair_distances<<<grid, 256, 0, (cudaStream_t)stream>>>(world, N, track_ids, vis_frames, frame_offsets,
+                                                                     pair_offsets, dist);
+  return check_launch("msp_track_all_pair_distances");
 }
 
 extern "C" int msp_draw_marks(uint8_t* images, int32_t B, int32_t H, int32_t W, const msp_mark* marks, int64_t M,

@@ -75,11 +75,40 @@ class Templates:
         cm = load("spatial_engine/camera_movement/TEMPLATES.py", "_msp_ref_cm_templates")
         t = dict(cls.NEUTRAL)
         t["camera_movement"] = {"task": cm.TASK_DESCRIPTION, "questions": cm.QUESTION_TEMPLATES, "answers": cm.ANSWER_TEMPLATES}
+        om = cls._literals(os.path.join(reference_root, "spatial_engine/object_movement/single_object_movement_engine_coord.py"),
+                           ("TASK_DESCRIPTION", "QUESTION_TEMPLATES", "ANSWER_TEMPLATES"))
+        for qt in om["QUESTION_TEMPLATES"]:
+            t[f"object_movement:{qt}"] = {"task": om["TASK_DESCRIPTION"], "questions": om["QUESTION_TEMPLATES"][qt],
+                                          "answers": om["ANSWER_TEMPLATES"][qt]}
         return cls(t)
+
+    @staticmethod
+    def _literals(path: str, names):
+        """Module-level template tables of a reference file WITHOUT importing it (the engine modules seed the global RNGs
+        and import optional packages when executed): only the assignments to ``names`` — plain ``NAME = literal`` and the
+        follow-up ``NAME[key] = [... for q in NAME[key]]`` rewrites — are evaluated, with no builtins in scope."""
+        import ast
+        tree = ast.parse(open(path).read())
+        ns = {"__builtins__": {}}
+        for node in tree.body:
+            if not (isinstance(node, ast.Assign) and len(node.targets) == 1):
+                continue
+            tgt = node.targets[0]
+            base = tgt.value if isinstance(tgt, ast.Subscript) else tgt
+            if isinstance(base, ast.Name) and base.id in names:
+                exec(compile(ast.Module([node], []), path, "exec"), ns)
+        missing = set(names) - set(ns)
+        if missing:
+            raise KeyError(f"{path}: no assignment for {sorted(missing)}")
+        return {k: ns[k] for k in names}
 
 
 def _pick(rng, seq):
-    return seq[int(rng.integers(0, len(seq)))]
+    """One element of ``seq``: a NumPy Generator draws an index; Python's ``random`` module (or a ``random.Random``)
+    is used through ``choice`` so that the draw consumes the reference's RNG stream exactly (it calls random.choice)."""
+    if hasattr(rng, "integers"):
+        return seq[int(rng.integers(0, len(seq)))]
+    return rng.choice(seq)
 
 
 def _conversation(task, question, answer):
@@ -349,7 +378,8 @@ def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="
     Static points (||dw|| < object_thr) get distance 0 and a zero vector (OM-coord:337-341); a triple whose point
     does not project inside either frame is skipped (OM-coord:360-362).
     """
-    tp = (templates or Templates()).t.get("object_movement", {
+    tabs = (templates or Templates()).t
+    tp = tabs.get(f"object_movement:{question_type}") or tabs.get("object_movement", {
         "task": ["Image-1: <image>\nImage-2: <image>\nCoordinates [ x , y ] are per-mille of width and height."],
         "questions": ["How far did the point at [ {x1} , {y1} ] in Image-1 move (mm), in camera-1 axes?"],
         "answers": ["`{total_distance}` [ {x_value} , {y_value} , {z_value} ]"]})
@@ -358,21 +388,25 @@ def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="
     tri = np.asarray(triples, np.int32).reshape(-1, 3)
     disp = vid.pair_displacement(tri).cpu().numpy()
     pm, ok = vid.permille.cpu().numpy(), vid.valid.cpu().numpy().astype(bool)
+    w2c_h = vid.w2c.cpu().numpy().reshape(-1, 4, 4)
     out = []
     for (f1, f2, pt), d in zip(tri.tolist(), disp):
         if not (ok[f1, pt] and ok[f2, pt]):
             continue
         moving = bool(d[0] >= object_thr)
-        dist, dcam = (float(d[0]), d[1:4].copy()) if moving else (0, np.zeros(3))
+        # a static point has its displacement zeroed BEFORE the rotation into camera-1 axes (OM-coord:337-341, 354-356):
+        # the product with a zero vector keeps IEEE signed zeros, which json.dumps shows ("-0.0")
+        dist, dcam = (float(d[0]), d[1:4].copy()) if moving else (0, (w2c_h[f1] @ np.zeros(4))[:3])
         x1, y1 = (int(v) for v in pm[f1, pt])
         x2, y2 = (int(v) for v in pm[f2, pt])
+        task = _pick(rng, tp["task"])                      # draw order of OM-coord:367-376: task, question, answer
         q = _pick(rng, tp["questions"]).format(x1=x1, y1=y1)
         ans = _pick(rng, tp["answers"]).format(total_distance=round(dist * 1000), x_value=round(float(dcam[0]) * 1000),
                                                y_value=round(float(dcam[1]) * 1000), z_value=round(float(dcam[2]) * 1000))
         if not moving:
             ans = "The point did not move. " + ans
         out.append({"id": f"{video_id}_{f1}_{f2}_{pt}", "image": [f"{video_id}/{f1:05d}.jpg", f"{video_id}/{f2:05d}.jpg"],
-                    "conversations": _conversation(_pick(rng, tp["task"]), q, ans), "height_list": [H, H], "width_list": [W, W],
+                    "conversations": _conversation(task, q, ans), "height_list": [H, H], "width_list": [W, W],
                     "gt_value": int(dist * 1000) if "total_distance" in question_type else dcam.tolist(),
                     "question_type": question_type, "point_moving": int(moving), "cam_moving": int(d[4] >= camera_thr),
                     "p1": (x1, y1), "p2": (x2, y2)})

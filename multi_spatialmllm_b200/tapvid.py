@@ -1,0 +1,181 @@
+"""TAPVid-3D object_movement: the per-video sample generation of the reference
+(single_object_movement_engine_coord.py:406-575, ``generate_qa_training_single_scene``) on the GPU path.
+
+  DeviceVideo.project                 world transform + pinhole projection of every (frame, track)     OM-coord:446-451, 293-315
+  DeviceVideo.rigid_body_groups       O(T N^2) distance-change accumulation on the device, linkage on host  OM-coord:49-105
+  sample_video_pairs                  all visible frame pairs of the chosen tracks -> distances on the device
+                                      (msp_track_all_pair_distances), static / moving split, 10-bin histogram sampling,
+                                      reverse augmentation                                              OM-coord:468-567
+  streams.object_movement_samples     two-frame samples in the reference JSONL schema                    OM-coord:317-404
+
+``sample_video_pairs`` consumes Python's ``random`` stream call for call like the reference (shuffle per group,
+random.choice of a static pair, random.sample per over-full bin, random.sample for the augmentation), so with the same
+seed it selects the same (point, frame1, frame2) triples; the Python loops of the reference (pair enumeration, per-pair
+np.digitize, list sorting) are replaced by array operations on the device distances.
+"""
+from __future__ import annotations
+
+import collections.abc
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import streams
+from ._lib import check, lib
+from .engine import DeviceVideo, _ptr, _stream
+
+OBJECT_NOT_MOVING_THRESHOLD = 0.01      # OM-coord:288
+CAMERA_NOT_MOVING_THRESHOLD = 0.01      # OM-coord:289
+
+
+class _Pairs(collections.abc.Sequence):
+    """(distance, frame1, frame2) tuples backed by arrays: random.choice / random.sample only need len() and indexing,
+    so the lists the reference builds in Python never have to exist."""
+
+    def __init__(self, dist, f1, f2):
+        self.dist, self.f1, self.f2 = dist, f1, f2
+
+    def __len__(self):
+        return len(self.dist)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return _Pairs(self.dist[i], self.f1[i], self.f2[i])
+        return (self.dist[i], self.f1[i], self.f2[i])
+
+
+def all_pair_distances(vid: DeviceVideo, track_ids, visible_frames):
+    """For each track its i<j visible-frame pairs (i-major, OM-coord:485-486) and their world-space distances
+    (OM-coord:492-495) computed on the device.  Returns a list of (dist float64 (P,), frame1 (P,), frame2 (P,))."""
+    if vid.world is None:
+        vid.project()
+    nt = len(track_ids)
+    if nt == 0:
+        return []
+    counts = np.array([len(v) for v in visible_frames], np.int64)
+    foff = np.zeros(nt + 1, np.int64)
+    foff[1:] = np.cumsum(counts)
+    npairs = counts * (counts - 1) // 2
+    poff = np.zeros(nt + 1, np.int64)
+    poff[1:] = np.cumsum(npairs)
+    dev = vid.device
+    dist = torch.empty(max(int(poff[-1]), 1), dtype=torch.float64, device=dev)
+    if poff[-1] > 0:
+        frames = torch.from_numpy(np.concatenate(visible_frames).astype(np.int32)).to(dev)
+        tid = torch.from_numpy(np.asarray(track_ids, np.int32)).to(dev)
+        foff_d, poff_d = torch.from_numpy(foff).to(dev), torch.from_numpy(poff).to(dev)
+        check(lib.msp_track_all_pair_distances(_ptr(vid.world), vid.T, vid.N, _ptr(tid), nt, _ptr(frames), _ptr(foff_d),
+                                               _ptr(poff_d), int(npairs.max()), _ptr(dist), _stream()),
+              "msp_track_all_pair_distances")
+    dist_h = dist.cpu().numpy()
+    out = []
+    for t in range(nt):
+        vf = np.asarray(visible_frames[t])
+        ii, jj = np.triu_indices(len(vf), k=1)
+        out.append((dist_h[poff[t]:poff[t + 1]], vf[ii], vf[jj]))
+    return out
+
+
+def sample_video_pairs(vid: DeviceVideo, visibility, groups, npoints_per_group=5, npairs_per_bin=1e8, augment=True,
+                       augment_ratio=1.0, object_thr=OBJECT_NOT_MOVING_THRESHOLD, rnd=random):
+    """OM-coord:468-567.  ``groups`` is shuffled in place like the reference's; ``rnd`` is the ``random`` module or a
+    ``random.Random``.  Returns [{"point_index", "frame1", "frame2"}, ...] in the reference's order.
+
+    Kept quirks: ``npairs_per_bin`` is overwritten by each track's middle-bin count and carries over to the following
+    tracks (OM-coord:535-538); the ``future_frame_windows`` test compares a distance with a frame index and never fires
+    (OM-coord:505-508)."""
+    visibility = np.asarray(visibility)
+    sample_pairs = []
+    for group in groups:
+        rnd.shuffle(group)
+        selected = group[:npoints_per_group]
+        vis = [np.where(visibility[:, p])[0] for p in selected]
+        keep = [k for k, v in enumerate(vis) if len(v) >= 2]
+        dists = all_pair_distances(vid, [selected[k] for k in keep], [vis[k] for k in keep])
+        for k, (d, f1, f2) in zip(keep, dists):
+            point_idx = selected[k]
+            static = d < object_thr
+            chosen = []
+            if static.any():
+                idx = np.flatnonzero(static)
+                chosen.append(rnd.choice(_Pairs(d[idx], f1[idx], f2[idx])))
+            if not static.all():
+                idx = np.flatnonzero(~static)
+                order = idx[np.argsort(d[idx], kind="stable")]          # list.sort(key=dist) is stable
+                ds, a, b = d[order], f1[order], f2[order]
+                edges = np.histogram_bin_edges(ds, bins=10)
+                # np.digitize(x, edges) - 1 capped at 9; the distances are sorted, so every bin is a contiguous run
+                cuts = np.concatenate([[0], np.searchsorted(ds, edges[1:10], side="left"), [len(ds)]])
+                bins = [_Pairs(ds[cuts[q]:cuts[q + 1]], a[cuts[q]:cuts[q + 1]], b[cuts[q]:cuts[q + 1]]) for q in range(10)]
+                npairs_per_bin = max(min(len(bins[4]), npairs_per_bin), 1)
+                for bn in bins:
+                    chosen.extend(rnd.sample(bn, npairs_per_bin) if len(bn) > npairs_per_bin else list(bn))
+            for _, fa, fb in chosen:
+                sample_pairs.append({"point_index": point_idx, "frame1": fa, "frame2": fb})
+    if augment:
+        for s in rnd.sample(sample_pairs, int(len(sample_pairs) * augment_ratio)):
+            sample_pairs.append({"point_index": s["point_index"], "frame1": s["frame2"], "frame2": s["frame1"]})
+    return sample_pairs
+
+
+def load_video(npz_path: str):
+    """The npz keys of the TAPVid-3D release (reference README.md:112-123, OM-coord:441-444)."""
+    gt = np.load(npz_path, allow_pickle=True)
+    if "extrinsics_w2c" not in gt.files:
+        raise NotImplementedError(f"{npz_path}: no extrinsics_w2c (camera-frame-only clips are not supported; ADT and "
+                                  "PStudio, the two subsets the reference lists, carry extrinsics)")
+    return {"images_jpeg_bytes": gt["images_jpeg_bytes"], "fx_fy_cx_cy": gt["fx_fy_cx_cy"], "tracks_XYZ": gt["tracks_XYZ"],
+            "visibility": gt["visibility"], "extrinsics_w2c": gt["extrinsics_w2c"]}
+
+
+def export_frames(images_jpeg_bytes, scene_img_dir: str):
+    """OM-coord:417-438: frames as %05d.jpg (skipped when the directory already holds them all).  The JPEG streams are
+    written verbatim (the reference decodes and re-encodes each one); returns (height, width)."""
+    import cv2
+    os.makedirs(scene_img_dir, exist_ok=True)
+    have = [f for f in os.listdir(scene_img_dir) if f.endswith(".jpg")]
+    if len(have) != len(images_jpeg_bytes):
+        for i, frame_bytes in enumerate(images_jpeg_bytes):
+            with open(os.path.join(scene_img_dir, f"{i:05d}.jpg"), "wb") as f:
+                f.write(bytes(frame_bytes))
+    img = cv2.imdecode(np.frombuffer(bytes(images_jpeg_bytes[0]), np.uint8), cv2.IMREAD_UNCHANGED)
+    return int(img.shape[0]), int(img.shape[1])
+
+
+def generate_video_samples(video, video_id: str, question_type="tapvid3d_total_distance", npoints_per_group=5,
+                           npairs_per_bin=1e8, img_output_dir=None, image_hw=None, augment=True, augment_ratio=1.0,
+                           templates=None, rnd=random, device="cuda:0"):
+    """generate_qa_training_single_scene (OM-coord:406-575) for one video (a dict as returned by ``load_video``)."""
+    if img_output_dir is not None:
+        image_hw = export_frames(video["images_jpeg_bytes"], os.path.join(img_output_dir, video_id))
+    elif image_hw is None:
+        import cv2
+        img = cv2.imdecode(np.frombuffer(bytes(video["images_jpeg_bytes"][0]), np.uint8), cv2.IMREAD_UNCHANGED)
+        image_hw = (int(img.shape[0]), int(img.shape[1]))
+    tracks = np.asarray(video["tracks_XYZ"])
+    vid = DeviceVideo(tracks.astype(np.float32), video["extrinsics_w2c"], video["fx_fy_cx_cy"], image_hw, device=device)
+    vid.project()
+    groups, _ = vid.rigid_body_groups()                               # OM-coord:454-455 (threshold 0.1, groups > 5 points)
+    pairs = sample_video_pairs(vid, video["visibility"], groups, npoints_per_group, npairs_per_bin, augment, augment_ratio,
+                               rnd=rnd)
+    triples = [(int(p["frame1"]), int(p["frame2"]), int(p["point_index"])) for p in pairs]
+    return streams.object_movement_samples(vid, video_id, triples, question_type, templates=templates, rng=rnd)
+
+
+def generate_split(npz_files, output_file: str, question_type="tapvid3d_total_distance", img_output_dir=None,
+                   npoints_per_group=5, npairs_per_bin=1e8, augment=True, augment_ratio=1.0, max_samples=-1, templates=None,
+                   seed=0, device="cuda:0"):
+    """generate_qa_training_data (OM-coord:580-610) for this rank's videos: every video draws from its own
+    ``random.Random(seed + index)`` (the reference's Pool workers each inherit the module-level seed), samples are
+    concatenated in file order, optionally sub-sampled to ``max_samples``, written as JSONL."""
+    out = []
+    for i, path in enumerate(npz_files):
+        vid_id = os.path.splitext(os.path.basename(path))[0]
+        out.extend(generate_video_samples(load_video(path), vid_id, question_type, npoints_per_group, npairs_per_bin,
+                                          img_output_dir, None, augment, augment_ratio, templates,
+                                          random.Random(seed + i), device))
+    if max_samples > 0 and len(out) > max_samples:
+        out = random.Random(seed).sample(out, max_samples)
+    return streams.write_jsonl(out, output_file)

@@ -1,0 +1,118 @@
+"""TAPVid-3D per-video sample generation (multi_spatialmllm_b200.tapvid) against the reference's own
+generate_qa_training_single_scene (OM-coord:406-575) on seeded synthetic clips — tests/golden/make_golden_tapvid_sampling.py.
+Parity bar: the same samples in the same order (ids, integers, float vectors bit-identical, conversation text) and the
+same position of Python's RNG stream afterwards."""
+import gzip
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden():
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "tapvid_sampling.json.gz"), "rt") as f:
+        return json.load(f)
+
+
+def _clip(seed, T, N, G):
+    from multi_spatialmllm_b200 import synth
+    v = synth.make_video(seed, n_frames=T, n_tracks=N, n_groups=G, image_hw=(36, 64))
+    v.tracks_xyz[:, : N // 6] = v.tracks_xyz[:1, : N // 6]
+    return v
+
+
+def test_pair_sequence_behaves_like_the_reference_lists_cpu():
+    """random.choice / random.sample on the array-backed sequence draw exactly what they draw on a list of tuples."""
+    from multi_spatialmllm_b200.tapvid import _Pairs
+    d, a, b = np.arange(50) * 0.5, np.arange(50), np.arange(50) + 1
+    seq, lst = _Pairs(d, a, b), list(zip(d, a, b))
+    for k in (1, 3, 7, 30, 50):
+        random.seed(k)
+        got = random.sample(seq, k)
+        random.seed(k)
+        assert got == random.sample(lst, k)
+    random.seed(5)
+    got = random.choice(seq)
+    random.seed(5)
+    assert got == random.choice(lst)
+    assert list(seq[3:5]) == lst[3:5] and len(seq[10:]) == 40
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case_index", [0, 1])
+def test_video_samples_match_reference(case_index, tmp_path):
+    from multi_spatialmllm_b200 import streams, tapvid
+    g = _golden()
+    case = g["cases"][case_index]
+    vs, T, N, G, qt, npg, ratio, rs = case["case"]
+    v = _clip(vs, T, N, G)
+    tp = streams.Templates({f"object_movement:{qt}": g["templates"]})
+    video = {"images_jpeg_bytes": None, "fx_fy_cx_cy": v.fxfycxcy, "tracks_XYZ": v.tracks_xyz, "visibility": v.visibility,
+             "extrinsics_w2c": v.w2c}
+    random.seed(rs)
+    out = tapvid.generate_video_samples(video, v.video_id, qt, npoints_per_group=npg, npairs_per_bin=1e8, image_hw=(36, 64),
+                                        augment=True, augment_ratio=ratio, templates=tp, rnd=random)
+    after = random.random()
+    want = case["samples"]
+    assert [e["id"] for e in out] == [w["id"] for w in want]
+    for e, w in zip(out, want):
+        assert e["gt_value"] == w["gt_value"], e["id"]                       # int mm, or the float64 vector bit for bit
+        assert list(e["p1"]) == w["p1"] and list(e["p2"]) == w["p2"]
+        assert (e["point_moving"], e["cam_moving"]) == (w["point_moving"], w["cam_moving"])
+        assert e["image"] == w["image"] and [e["height_list"][0], e["width_list"][0]] == w["hw"]
+        assert e["conversations"] == w["conversations"], e["id"]
+        assert e["question_type"] == qt
+    assert after == case["random_after"]                                      # same number and kind of draws
+    assert sum(w["point_moving"] == 0 for w in want) > 0 and json.dumps(out[0])
+
+
+@pytest.mark.gpu
+def test_all_pair_distances_numpy_order():
+    """msp_track_all_pair_distances == np.linalg.norm(p2 - p1, axis=1) bit for bit, pairs in i-major order, ragged tracks."""
+    from multi_spatialmllm_b200 import tapvid
+    from multi_spatialmllm_b200.engine import DeviceVideo
+    v = _clip(3, 40, 32, 3)
+    vid = DeviceVideo(v.tracks_xyz, v.w2c, v.fxfycxcy, (36, 64)).project()
+    world = vid.world.cpu().numpy()
+    rng = np.random.default_rng(0)
+    tracks = [5, 0, 17, 31]
+    vis = [np.sort(rng.choice(40, k, replace=False)) for k in (40, 2, 13, 0)]
+    res = tapvid.all_pair_distances(vid, tracks, vis)
+    assert len(res) == 4
+    for t, vf, (d, f1, f2) in zip(tracks, vis, res):
+        pairs = [(i, j) for i in range(len(vf)) for j in range(i + 1, len(vf))]          # OM-coord:485-486
+        assert len(d) == len(pairs)
+        if pairs:
+            fp = np.array(pairs)
+            np.testing.assert_array_equal(f1, vf[fp[:, 0]])
+            np.testing.assert_array_equal(f2, vf[fp[:, 1]])
+            np.testing.assert_array_equal(d, np.linalg.norm(world[f2, t] - world[f1, t], axis=1))
+    assert tapvid.all_pair_distances(vid, [], []) == []
+
+
+@pytest.mark.gpu
+def test_generate_split_writes_jsonl(tmp_path):
+    import cv2
+    from multi_spatialmllm_b200 import tapvid
+    files = []
+    for seed in (21, 22):
+        v = _clip(seed, 16, 36, 2)
+        ok, jpg = cv2.imencode(".jpg", np.zeros((36, 64, 3), np.uint8))
+        p = str(tmp_path / f"{v.video_id}.npz")
+        np.savez(p, images_jpeg_bytes=np.array([jpg.tobytes()] * 16, dtype=object), fx_fy_cx_cy=v.fxfycxcy,
+                 tracks_XYZ=v.tracks_xyz, visibility=v.visibility, extrinsics_w2c=v.w2c)
+        files.append(p)
+    out = str(tmp_path / "om.jsonl")
+    n = tapvid.generate_split(files, out, img_output_dir=str(tmp_path / "img"), max_samples=150)
+    rows = [json.loads(l) for l in open(out)]
+    assert n == len(rows) == 150
+    assert os.path.exists(tmp_path / "img" / "video00021" / "00015.jpg")
+    assert all(r["height_list"] == [36, 36] and r["width_list"] == [64, 64] for r in rows)
+    np.savez(str(tmp_path / "noext.npz"), images_jpeg_bytes=np.array([b""], dtype=object), fx_fy_cx_cy=np.ones(4),
+             tracks_XYZ=np.zeros((1, 1, 3)), visibility=np.ones((1, 1), bool))
+    with pytest.raises(NotImplementedError):
+        tapvid.load_video(str(tmp_path / "noext.npz"))
