@@ -371,13 +371,12 @@ def camera_movement_samples(sc, scene_id, image_ids, pairs, question_type, start
     return out
 
 
-def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="tapvid3d_total_distance",
-                            object_thr=0.01, camera_thr=0.01, templates=None, rng=None):
-    """TAPVid-3D two-frame samples for (frame1, frame2, track) triples (OM-coord:317-404).
+def _randint(rng, lo, hi):
+    """random.randint(lo, hi) on either kind of generator (inclusive bounds)."""
+    return int(rng.integers(lo, hi + 1)) if hasattr(rng, "integers") else rng.randint(lo, hi)
 
-    Static points (||dw|| < object_thr) get distance 0 and a zero vector (OM-coord:337-341); a triple whose point
-    does not project inside either frame is skipped (OM-coord:360-362).
-    """
+
+def _object_movement(vid: DeviceVideo, video_id, triples, question_type, object_thr, camera_thr, templates, rng, dot, seen):
     tabs = (templates or Templates()).t
     tp = tabs.get(f"object_movement:{question_type}") or tabs.get("object_movement", {
         "task": ["Image-1: <image>\nImage-2: <image>\nCoordinates [ x , y ] are per-mille of width and height."],
@@ -388,8 +387,9 @@ def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="
     tri = np.asarray(triples, np.int32).reshape(-1, 3)
     disp = vid.pair_displacement(tri).cpu().numpy()
     pm, ok = vid.permille.cpu().numpy(), vid.valid.cpu().numpy().astype(bool)
+    uvn = vid.uvn.cpu().numpy() if dot else None
     w2c_h = vid.w2c.cpu().numpy().reshape(-1, 4, 4)
-    out = []
+    out, marks, plan = [], [], []
     for (f1, f2, pt), d in zip(tri.tolist(), disp):
         if not (ok[f1, pt] and ok[f2, pt]):
             continue
@@ -405,12 +405,46 @@ def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="
                                                y_value=round(float(dcam[1]) * 1000), z_value=round(float(dcam[2]) * 1000))
         if not moving:
             ans = "The point did not move. " + ans
-        out.append({"id": f"{video_id}_{f1}_{f2}_{pt}", "image": [f"{video_id}/{f1:05d}.jpg", f"{video_id}/{f2:05d}.jpg"],
+        if dot:
+            # OM-dot:408-425: image 1 gets one filled circle of radius W // 100 at (int(u_n * W), int(v_n * H)) in a colour
+            # drawn from the RNG the first time this (frame, point) is annotated; image 2 is a plain copy
+            if (f1, pt) not in seen:
+                seen.add((f1, pt))
+                color = tuple(_randint(rng, 0, 255) for _ in range(3))                 # generate_distinct_colors(1), OM-dot:38-49
+                _mark(marks, len(plan), (int(uvn[f1, pt, 0] * W), int(uvn[f1, pt, 1] * H)), color, radius=W // 100)
+                plan.append((f1, f"{video_id}/{f1:05d}_{pt}_annotated.jpg"))
+            images = [f"{video_id}/{f1:05d}_{pt}_annotated.jpg", f"{video_id}/{f2:05d}.jpg"]
+            vector_gt = question_type != "total_distance"   # OM-dot:435 tests the bare name: always the vector for tapvid3d_* types
+        else:
+            images = [f"{video_id}/{f1:05d}.jpg", f"{video_id}/{f2:05d}.jpg"]
+            vector_gt = "total_distance" not in question_type
+        out.append({"id": f"{video_id}_{f1}_{f2}_{pt}" + ("_ann" if dot else ""), "image": images,
                     "conversations": _conversation(task, q, ans), "height_list": [H, H], "width_list": [W, W],
-                    "gt_value": int(dist * 1000) if "total_distance" in question_type else dcam.tolist(),
+                    "gt_value": dcam.tolist() if vector_gt else int(dist * 1000),
                     "question_type": question_type, "point_moving": int(moving), "cam_moving": int(d[4] >= camera_thr),
                     "p1": (x1, y1), "p2": (x2, y2)})
-    return out
+    return out, marks, plan
+
+
+def object_movement_samples(vid: DeviceVideo, video_id, triples, question_type="tapvid3d_total_distance",
+                            object_thr=0.01, camera_thr=0.01, templates=None, rng=None):
+    """TAPVid-3D two-frame samples for (frame1, frame2, track) triples (OM-coord:317-404).
+
+    Static points (||dw|| < object_thr) get distance 0 and a zero vector (OM-coord:337-341); a triple whose point
+    does not project inside either frame is skipped (OM-coord:360-362).  ``rng``: a NumPy Generator, or Python's
+    ``random`` module / a ``random.Random`` to consume the reference's RNG stream draw for draw.
+    """
+    return _object_movement(vid, video_id, triples, question_type, object_thr, camera_thr, templates, rng, False, None)[0]
+
+
+def object_movement_dot_samples(vid: DeviceVideo, video_id, triples, question_type="tapvid3d_total_distance",
+                                object_thr=0.01, camera_thr=0.01, templates=None, rng=None, seen=None):
+    """The dot variant (single_object_movement_engine_dot.py:341-441).  Returns (samples, marks, plan): annotated image k
+    is frame ``plan[k][0]`` with ``marks[marks["image"] == k]`` painted on it, to be stored as ``plan[k][1]``; ``seen``
+    carries the (frame, point) images already annotated (the reference skips files that exist, OM-dot:417-421)."""
+    seen = set() if seen is None else seen
+    out, marks, plan = _object_movement(vid, video_id, triples, question_type, object_thr, camera_thr, templates, rng, True, seen)
+    return out, _finish_marks(marks), plan
 
 
 def object_perception_samples(scene_id, image_hw, dimension_name, object_dims_m, object_categories, coverage_by_object,

@@ -144,11 +144,41 @@ def export_frames(images_jpeg_bytes, scene_img_dir: str):
     return int(img.shape[0]), int(img.shape[1])
 
 
+def render_dot_images(video, video_id: str, samples, marks, plan, img_output_dir: str, device="cuda:0", batch=64) -> int:
+    """OM-dot:408-425: write ``<frame1>_<point>_annotated.jpg`` (decode on nvJPEG, one filled circle painted by
+    msp_draw_marks, encode on nvJPEG) and a plain copy of every second frame.  Returns the number of files written."""
+    from . import annotate
+    out_dir = os.path.join(img_output_dir, video_id)
+    os.makedirs(out_dir, exist_ok=True)
+    written = 0
+    for k0 in range(0, len(plan), batch):
+        chunk = plan[k0:k0 + batch]
+        imgs = torch.stack([annotate.jpeg_decode(bytes(video["images_jpeg_bytes"][f]), device) for f, _ in chunk]).contiguous()
+        m = marks[(marks["image"] >= k0) & (marks["image"] < k0 + len(chunk))].copy()
+        m["image"] -= k0
+        annotate.draw_marks(imgs, m)
+        for img, (_, rel) in zip(imgs, chunk):
+            with open(os.path.join(img_output_dir, rel), "wb") as f:
+                f.write(annotate.jpeg_encode(img))
+            written += 1
+    for s in samples:                                        # image 2 is not annotated: the original JPEG stream, verbatim
+        path = os.path.join(img_output_dir, s["image"][1])
+        if not os.path.exists(path):
+            frame = int(os.path.basename(path).split(".")[0])
+            with open(path, "wb") as f:
+                f.write(bytes(video["images_jpeg_bytes"][frame]))
+            written += 1
+    return written
+
+
 def generate_video_samples(video, video_id: str, question_type="tapvid3d_total_distance", npoints_per_group=5,
                            npairs_per_bin=1e8, img_output_dir=None, image_hw=None, augment=True, augment_ratio=1.0,
-                           templates=None, rnd=random, device="cuda:0"):
-    """generate_qa_training_single_scene (OM-coord:406-575) for one video (a dict as returned by ``load_video``)."""
-    if img_output_dir is not None:
+                           templates=None, rnd=random, device="cuda:0", dot=False, object_thr=OBJECT_NOT_MOVING_THRESHOLD,
+                           camera_thr=CAMERA_NOT_MOVING_THRESHOLD):
+    """generate_qa_training_single_scene for one video (a dict as returned by ``load_video``): OM-coord:406-575, or with
+    ``dot=True`` single_object_movement_engine_dot.py:448-616 (annotated first image, ids ending in ``_ann``; the
+    annotated JPEGs go to ``img_output_dir``).  Drivetrack's looser thresholds (OM-dot:301-302) are the two ``*_thr``."""
+    if img_output_dir is not None and not dot:
         image_hw = export_frames(video["images_jpeg_bytes"], os.path.join(img_output_dir, video_id))
     elif image_hw is None:
         import cv2
@@ -159,14 +189,21 @@ def generate_video_samples(video, video_id: str, question_type="tapvid3d_total_d
     vid.project()
     groups, _ = vid.rigid_body_groups()                               # OM-coord:454-455 (threshold 0.1, groups > 5 points)
     pairs = sample_video_pairs(vid, video["visibility"], groups, npoints_per_group, npairs_per_bin, augment, augment_ratio,
-                               rnd=rnd)
+                               object_thr=object_thr, rnd=rnd)
     triples = [(int(p["frame1"]), int(p["frame2"]), int(p["point_index"])) for p in pairs]
-    return streams.object_movement_samples(vid, video_id, triples, question_type, templates=templates, rng=rnd)
+    if not dot:
+        return streams.object_movement_samples(vid, video_id, triples, question_type, object_thr, camera_thr,
+                                               templates=templates, rng=rnd)
+    samples, marks, plan = streams.object_movement_dot_samples(vid, video_id, triples, question_type, object_thr, camera_thr,
+                                                               templates=templates, rng=rnd)
+    if img_output_dir is not None:
+        render_dot_images(video, video_id, samples, marks, plan, img_output_dir, device)
+    return samples
 
 
 def generate_split(npz_files, output_file: str, question_type="tapvid3d_total_distance", img_output_dir=None,
                    npoints_per_group=5, npairs_per_bin=1e8, augment=True, augment_ratio=1.0, max_samples=-1, templates=None,
-                   seed=0, device="cuda:0"):
+                   seed=0, device="cuda:0", dot=False):
     """generate_qa_training_data (OM-coord:580-610) for this rank's videos: every video draws from its own
     ``random.Random(seed + index)`` (the reference's Pool workers each inherit the module-level seed), samples are
     concatenated in file order, optionally sub-sampled to ``max_samples``, written as JSONL."""
@@ -175,7 +212,7 @@ def generate_split(npz_files, output_file: str, question_type="tapvid3d_total_di
         vid_id = os.path.splitext(os.path.basename(path))[0]
         out.extend(generate_video_samples(load_video(path), vid_id, question_type, npoints_per_group, npairs_per_bin,
                                           img_output_dir, None, augment, augment_ratio, templates,
-                                          random.Random(seed + i), device))
+                                          random.Random(seed + i), device, dot))
     if max_samples > 0 and len(out) > max_samples:
         out = random.Random(seed).sample(out, max_samples)
     return streams.write_jsonl(out, output_file)

@@ -77,8 +77,44 @@ def main():
                      "conversations": e["conversations"]} for e in data]
             out.append({"case": [vs, T, N, G, qt, npg, ratio, rs], "samples": rows, "random_after": after})
             print(qt, len(rows), "samples;", sum(r["point_moving"] == 0 for r in rows), "static")
+    # ---- dot variant (single_object_movement_engine_dot.py): same sampling, first image annotated; cv2.circle is wrapped
+    #      (the library call, not the reference) to record centre / radius / colour of every annotation in order
+    with quiet:
+        from spatial_engine.object_movement import single_object_movement_engine_dot as omd
+    dot_cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for (vs, T, N, G, qt, npg, ratio, rs) in [(13, 20, 40, 2, "tapvid3d_displacement_vector", 2, 0.3, 3)]:
+            v = make_clip(vs, T, N, G)
+            path = os.path.join(tmp, f"{v.video_id}.npz")
+            write_npz(path, v)
+            eng = omd.TwoFrameVideoQAEngineDot(qt, "adt")
+            eng.task_description, eng.question_templates, eng.answer_templates = (TEMPLATES["task"], TEMPLATES["questions"],
+                                                                                 TEMPLATES["answers"])
+            circles, real_circle = [], cv2.circle
+
+            def spy(img, center, radius, color, thickness=1, *a, **k):
+                circles.append([int(center[0]), int(center[1]), int(radius), [int(c) for c in color], int(thickness)])
+                return real_circle(img, center, radius, color, thickness, *a, **k)
+
+            omd.cv2.circle = spy
+            random.seed(rs)
+            try:
+                with quiet:
+                    data = eng.generate_qa_training_single_scene(path, os.path.join(tmp, "base"), npoints_per_group=npg,
+                                                                 npairs_per_bin=1e8, img_output_dir=os.path.join(tmp, "ann"),
+                                                                 augment=True, augment_ratio=ratio)
+            finally:
+                omd.cv2.circle = real_circle
+            after = random.random()
+            rows = [{"id": e["id"], "gt_value": e["gt_value"], "p1": list(e["p1"]), "p2": list(e["p2"]),
+                     "point_moving": e["point_moving"], "cam_moving": e["cam_moving"], "image": e["image"],
+                     "hw": [e["height_list"][0], e["width_list"][0]], "conversations": e["conversations"]} for e in data]
+            files = sorted(os.listdir(os.path.join(tmp, "ann", v.video_id)))
+            dot_cases.append({"case": [vs, T, N, G, qt, npg, ratio, rs], "samples": rows, "random_after": after,
+                              "circles": circles, "files": files})
+            print("dot", qt, len(rows), "samples;", len(circles), "annotated images;", len(files), "files")
     with gzip.open(os.path.join(HERE, "tapvid_sampling.json.gz"), "wt") as f:
-        json.dump({"templates": TEMPLATES, "cases": out}, f)
+        json.dump({"templates": TEMPLATES, "cases": out, "dot_cases": dot_cases}, f)
 
 
 if __name__ == "__main__":

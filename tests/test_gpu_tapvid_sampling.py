@@ -116,3 +116,52 @@ def test_generate_split_writes_jsonl(tmp_path):
              tracks_XYZ=np.zeros((1, 1, 3)), visibility=np.ones((1, 1), bool))
     with pytest.raises(NotImplementedError):
         tapvid.load_video(str(tmp_path / "noext.npz"))
+
+
+@pytest.mark.gpu
+def test_dot_variant_matches_reference(tmp_path):
+    """single_object_movement_engine_dot.py: same triples, `_ann` ids, vector gt (its question_type test never matches),
+    one circle per first-seen (frame, point) with the colour drawn from the RNG; files written with the reference's names."""
+    import cv2
+    from multi_spatialmllm_b200 import streams, tapvid
+    g = _golden()
+    case = g["dot_cases"][0]
+    vs, T, N, G, qt, npg, ratio, rs = case["case"]
+    v = _clip(vs, T, N, G)
+    ok, jpg = cv2.imencode(".jpg", np.full((36, 64, 3), 90, np.uint8))
+    video = {"images_jpeg_bytes": np.array([jpg.tobytes()] * T, dtype=object), "fx_fy_cx_cy": v.fxfycxcy,
+             "tracks_XYZ": v.tracks_xyz, "visibility": v.visibility, "extrinsics_w2c": v.w2c}
+    tp = streams.Templates({f"object_movement:{qt}": g["templates"]})
+    # marks first (no rendering), to compare every circle with the reference's cv2.circle calls
+    from multi_spatialmllm_b200.engine import DeviceVideo
+    random.seed(rs)
+    vid = DeviceVideo(v.tracks_xyz, v.w2c, v.fxfycxcy, (36, 64)).project()
+    groups, _ = vid.rigid_body_groups()
+    pairs = tapvid.sample_video_pairs(vid, v.visibility, groups, npg, 1e8, True, ratio, rnd=random)
+    tri = [(int(p["frame1"]), int(p["frame2"]), int(p["point_index"])) for p in pairs]
+    samples, marks, plan = streams.object_movement_dot_samples(vid, v.video_id, tri, qt, templates=tp, rng=random)
+    assert random.random() == case["random_after"]
+    want = case["samples"]
+    assert [e["id"] for e in samples] == [w["id"] for w in want]
+    for e, w in zip(samples, want):
+        assert e["gt_value"] == w["gt_value"] and e["image"] == w["image"] and e["conversations"] == w["conversations"]
+        assert list(e["p1"]) == w["p1"] and list(e["p2"]) == w["p2"]
+        assert (e["point_moving"], e["cam_moving"]) == (w["point_moving"], w["cam_moving"])
+    got_circles = [[int(m["x"]), int(m["y"]), int(m["radius"]), [int(c) for c in m["bgr"]], -1] for m in marks]
+    assert got_circles == case["circles"]                                     # centre, radius W//100, colour, filled
+    assert len(plan) == len(case["circles"])
+    # end to end with rendering: the reference's file set, decodable images with the dot where it belongs
+    random.seed(rs)
+    out = tapvid.generate_video_samples(video, v.video_id, qt, npoints_per_group=npg, image_hw=(36, 64), augment=True,
+                                        augment_ratio=ratio, templates=tp, rnd=random, dot=True,
+                                        img_output_dir=str(tmp_path / "ann"))
+    assert [e["id"] for e in out] == [w["id"] for w in want]
+    assert sorted(os.listdir(tmp_path / "ann" / v.video_id)) == case["files"]
+    m0 = marks[0]
+    img = cv2.imread(str(tmp_path / "ann" / plan[0][1]))
+    assert img.shape == (36, 64, 3)
+    if 0 <= m0["x"] < 64 and 0 <= m0["y"] < 36 and m0["radius"] >= 0:
+        # radius W // 100 = 0: a single pixel, blurred by the JPEG round trip but clearly pulled towards the colour
+        px = img[m0["y"], m0["x"]].astype(int)
+        assert np.abs(px - m0["bgr"].astype(int)).sum() < np.abs(np.array([90, 90, 90]) - m0["bgr"].astype(int)).sum() or \
+            np.abs(np.array([90, 90, 90]) - m0["bgr"].astype(int)).sum() < 60
