@@ -319,3 +319,110 @@ def object_coverage_scene(scene_infos, scene_id: str, sc: "engine.DeviceScene", 
                                                            float(target), COVERAGE_TOLERANCE, max_images=max_images)
         out[object_id] = res
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the three L2 scripts' main(): reference default paths, one process per GPU under torchrun
+# ------------------------------------------------------------------------------------------------
+L2_DEFAULTS = {                                        # MVI:190-206, CFR:257-268, COV:199-210
+    "visibility": {"train": "data/scannet/scannet_instance_data/train_visibility_info_D5.parquet",
+                   "val": "data/scannet/scannet_instance_data/val_visibility_info_D5.parquet"},
+    "relations": {"train": "training_data/camera_movement/train_camera_info_D5.parquet",
+                  "val": "evaluation_data/camera_movement/val_camera_info_D5.parquet"},
+    "object_visibility": {"train": "training_data/object_perception/object_visibility.pkl",
+                          "val": "evaluation_data/object_perception/object_visibility.pkl"},
+}
+L2_INFO = {"train": "data/scannet/scannet_instance_data/scenes_train_info_i_D5.pkl",
+           "val": "data/scannet/scannet_instance_data/scenes_val_info_i_D5.pkl"}
+
+
+def merge_parquet_parts(part_files, output_file: str, scene_order, scene_of=None) -> int:
+    """Concatenate the per-rank part files (one row group per scene) into ``output_file`` with the scenes in
+    ``scene_order`` — the row order the single-process run (and the reference) produces.  ``scene_of`` maps the first row
+    of a row group to its scene id (default: the ``scene_id`` column, else the ``key`` prefix)."""
+    import pyarrow.parquet as pq
+    where = {}
+    files = [pq.ParquetFile(p) for p in part_files if os.path.exists(p)]
+    for pf in files:
+        col = "scene_id" if "scene_id" in pf.schema_arrow.names else "key"
+        for g in range(pf.num_row_groups):
+            first = pf.read_row_group(g, columns=[col]).column(0)[0].as_py()
+            sid = scene_of(first) if scene_of else (first if col == "scene_id" else first.split(":", 1)[0])
+            where.setdefault(sid, []).append((pf, g))
+    rows, writer = 0, None
+    for sid in scene_order:
+        for pf, g in where.get(sid, []):
+            t = pf.read_row_group(g)
+            if writer is None:
+                writer = pq.ParquetWriter(output_file, t.schema)
+            writer.write_table(t)
+            rows += t.num_rows
+    if writer is not None:
+        writer.close()
+    return rows
+
+
+def main(argv=None):
+    """``python -m multi_spatialmllm_b200.tables {visibility,relations,object_visibility}`` = the ``main()`` of
+    make_visibility_info.py, calculate_frames_relations.py and compute_object_visibility.py (val split, then train, the
+    reference's default paths).  Under ``torchrun`` every rank takes a cost-balanced share of the scenes (shard.py), writes
+    its own part file, and rank 0 merges the parts in scene order after one host-side gather — no device collective."""
+    import argparse
+    from . import shard
+    from .handler.info_handler import SceneInfoHandler
+    ap = argparse.ArgumentParser()
+    ap.add_argument("table", choices=sorted(L2_DEFAULTS))
+    ap.add_argument("--splits", default="val,train")
+    ap.add_argument("--train_info_path", default=L2_INFO["train"])
+    ap.add_argument("--val_info_path", default=L2_INFO["val"])
+    ap.add_argument("--train_output", default=None)
+    ap.add_argument("--val_output", default=None)
+    ap.add_argument("--posed_images_root", default="data/scannet/posed_images")
+    ap.add_argument("--instance_data_root", default="data/scannet/scannet_instance_data")
+    a = ap.parse_args(argv)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")                  # host-side gather only
+    run = {"visibility": run_visibility_split, "relations": run_relations_split,
+           "object_visibility": run_object_visibility_split}[a.table]
+    results = {}
+    for split in a.splits.split(","):
+        h = SceneInfoHandler(getattr(a, f"{split}_info_path"), posed_images_root=a.posed_images_root,
+                             instance_data_root=a.instance_data_root)
+        out = getattr(a, f"{split}_output") or L2_DEFAULTS[a.table][split]
+        os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
+        scene_ids = h.get_all_scene_ids()
+        if world == 1:
+            results[split] = run(h, out, device=device)
+            continue
+        costs = {s: shard.scene_cost(len(h.get_scene_points_align(s)), h.get_num_posed_images(s)) for s in scene_ids}
+        mine = set(shard.my_shard(costs, rank, world))
+        part = shard.part_path(out, rank)
+        res = run(h, part, scene_ids=[s for s in scene_ids if s in mine], device=device)
+        man = shard.gather_manifest({"rank": rank, "part": part, "scenes": len(mine)})
+        if rank == 0:
+            parts = [m["part"] for m in man]
+            if a.table == "object_visibility":
+                merged = {}
+                for p in parts:
+                    with open(p, "rb") as f:
+                        merged.update(pickle.load(f))
+                with open(out, "wb") as f:
+                    pickle.dump({s: merged[s] for s in scene_ids if s in merged}, f)
+                res = {"scenes": len(merged), "file": out}
+            else:
+                res = {"rows": merge_parquet_parts(parts, out, scene_ids), "file": out}
+                if a.table == "relations":
+                    nz = [p.replace(".parquet", "_nonzero.parquet") for p in parts]
+                    res["rows_nonzero"] = merge_parquet_parts(nz, out.replace(".parquet", "_nonzero.parquet"), scene_ids)
+        results[split] = res
+        import torch.distributed as dist
+        dist.barrier()
+    return results
+
+
+if __name__ == "__main__":
+    main()

@@ -271,3 +271,25 @@ def test_pair_engine_cli(disk, relations, tmp_path, monkeypatch):
     d = tmp_path / "training_data/camera_movement/v1_0"
     assert sorted(os.listdir(d)) == sorted(f"{q}_train.jsonl" for q in pair_engines.CAMERA_QUESTION_TYPES)
     assert len(open(d / "total_distance_train.jsonl").readlines()) == 12
+
+
+@pytest.mark.gpu
+def test_l2_tables_cli_single_rank(disk, relations, tmp_path):
+    """`python -m multi_spatialmllm_b200.tables <table>`: the main() of MVI / CFR / COV on one GPU; the relations file is
+    the one the split driver writes, the visibility file is readable by VisibilityInfoHandler."""
+    from multi_spatialmllm_b200 import tables
+    from multi_spatialmllm_b200.handler.info_handler import VisibilityInfoHandler
+    scenes, _, root, info = disk
+    common = ["--splits", "val", "--val_info_path", info, "--posed_images_root", os.path.join(root, "posed_images"),
+              "--instance_data_root", os.path.join(root, "scannet_instance_data")]
+    res = tables.main(["relations", *common, "--val_output", str(tmp_path / "cam.parquet")])
+    assert res["val"]["rows"] == len(pd.read_parquet(relations))
+    pd.testing.assert_frame_equal(pd.read_parquet(tmp_path / "cam.parquet"), pd.read_parquet(relations))
+    tables.main(["visibility", *common, "--val_output", str(tmp_path / "vis.parquet")])
+    v = VisibilityInfoHandler(str(tmp_path / "vis.parquet"))
+    ids = v.get_image_to_points_info(scenes[1].scene_id, scenes[1].image_ids[2])
+    assert ids == sorted(ids) and len(ids) > 0
+    tables.main(["object_visibility", *common, "--val_output", str(tmp_path / "ov.pkl")])
+    with open(tmp_path / "ov.pkl", "rb") as f:
+        ov = pickle.load(f)
+    assert list(ov) == [s.scene_id for s in scenes] and all("object_to_images" in x for x in ov.values())
