@@ -138,3 +138,67 @@ def jpeg_encode(image: torch.Tensor, quality: int = 95) -> bytes:
         check(lib.msp_jpeg_encode_bgr(image.data_ptr(), H, W, int(quality), out.ctypes.data, out.size, C.byref(n), _stream()),
               "msp_jpeg_encode_bgr")
     return out[:n.value].tobytes()
+
+
+_pool, _pool_size, _tls = None, 0, None
+
+
+def _worker_pool(workers: int):
+    """One long-lived pool: nvJPEG keeps a handle per host thread (msp_jpeg.inl), created on the thread's first call and
+    worth ~0.1 s — short-lived threads would pay it again and again."""
+    global _pool, _pool_size, _tls
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    if _pool is None or _pool_size < workers:
+        if _pool is not None:
+            _pool.shutdown(wait=True)
+        _pool, _pool_size, _tls = ThreadPoolExecutor(workers, thread_name_prefix="msp-jpeg"), workers, threading.local()
+    return _pool
+
+
+def write_annotated(jobs, read_source, output_dir: str, device="cuda:0", workers: int = 4, batch: int = 16) -> int:
+    """The ``cv2.imread -> cv2.circle / cv2.putText -> cv2.imwrite`` tail of the dot engines for a list of jobs
+    ``(source key, output path relative to output_dir, [mark tuples without the image index])``.
+
+    Every distinct source frame is decoded ONCE (nvJPEG), replicated on the device for the jobs that annotate it, painted
+    by one ``msp_draw_marks`` launch per batch and encoded per output (nvJPEG; the reference decodes and encodes per
+    sample).  ``workers`` host threads, each with its own CUDA stream and nvJPEG state, share the sources between them:
+    the Huffman stages of nvJPEG's decode and encode run on the host and release the GIL."""
+    _require_cuda()
+    if not jobs:
+        return 0
+    by_source = {}
+    for key, path, marks in jobs:
+        by_source.setdefault(key, []).append((path, marks))
+    sources = list(by_source.items())
+    for path in {os.path.dirname(os.path.join(output_dir, p)) for _, p, _ in jobs}:
+        os.makedirs(path, exist_ok=True)
+
+    def work(share, own_stream=True):
+        with torch.cuda.device(device):
+            if own_stream:
+                if getattr(_tls, "stream", None) is None or _tls.stream.device != torch.device(device):
+                    _tls.stream = torch.cuda.Stream(device)
+                stream = _tls.stream
+            else:
+                stream = torch.cuda.current_stream()
+            with torch.cuda.stream(stream):
+                for key, outs in share:
+                    src = jpeg_decode(read_source(key), device)
+                    for k0 in range(0, len(outs), batch):
+                        chunk = outs[k0:k0 + batch]
+                        stack = src.unsqueeze(0).repeat(len(chunk), 1, 1, 1)
+                        rows = [(n, *m) for n, (_, marks) in enumerate(chunk) for m in marks]
+                        if rows:
+                            draw_marks(stack, np.array(rows, dtype=MARK_DTYPE))
+                        for n, (path, _) in enumerate(chunk):
+                            with open(os.path.join(output_dir, path), "wb") as f:
+                                f.write(jpeg_encode(stack[n]))
+        return len(share)
+
+    workers = max(1, min(workers, len(sources)))
+    if workers == 1:
+        work(sources, own_stream=False)
+    else:
+        list(_worker_pool(workers).map(work, [sources[w::workers] for w in range(workers)]))
+    return len(jobs)

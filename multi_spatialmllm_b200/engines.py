@@ -154,24 +154,13 @@ class _DepthEngine:
 
     def _flush_images(self, scene_id):
         """Paint and write the annotated JPEGs queued for ``scene_id`` (cv2.imread / circle / putText / imwrite of the dot
-        engines) on the device: nvJPEG decode, msp_draw_marks, nvJPEG encode."""
+        engines) on the device: annotate.write_annotated (nvJPEG decode once per frame, msp_draw_marks, nvJPEG encode)."""
         if not self.pending_marks:
             return
-        import torch
         from . import annotate
-        from .annotate import MARK_DTYPE
-        out_dir = os.path.join(self.image_output_dir, scene_id)
-        os.makedirs(out_dir, exist_ok=True)
         jobs, self.pending_marks = self.pending_marks, []
-        for k0 in range(0, len(jobs), 32):
-            chunk = jobs[k0:k0 + 32]
-            imgs = torch.stack([annotate.jpeg_decode(open(self.scene_info.get_image_path(scene_id, image_id), "rb").read(),
-                                                     self.device) for image_id, _, _ in chunk]).contiguous()
-            rows = [(k, *m) for k, (_, _, marks) in enumerate(chunk) for m in marks]
-            annotate.draw_marks(imgs, np.array(rows, dtype=MARK_DTYPE))
-            for img, (_, name, _) in zip(imgs, chunk):
-                with open(os.path.join(out_dir, name), "wb") as f:
-                    f.write(annotate.jpeg_encode(img))
+        annotate.write_annotated(jobs, lambda image_id: open(self.scene_info.get_image_path(scene_id, image_id), "rb").read(),
+                                 os.path.join(self.image_output_dir, scene_id), self.device)
 
     # -- the reference's split drivers (DE-coor:256-312; identical in the other three files)
     def generate_qa_training_data(self, output_dir, save_file=True):

@@ -481,30 +481,14 @@ class VisualCorrespondenceDotEngine(_VisualCorrespondence):
                 "height_list": [H] * 2, "width_list": [W] * 2, "question_type": "visual_correspondence_multiple_choice",
                 "gt_value": correct_label, "p1_list": [u1, v1], "p2_list": [correct] + incorrect}, as_predicted
 
-    def flush_images(self, image_output_dir, batch=32):
-        """cv2.imread / circle / putText / imwrite of VC-dot:358-395 for every queued sample."""
-        if not self.pending_marks:
-            return 0
-        import torch
+    def flush_images(self, image_output_dir, workers=4):
+        """cv2.imread / circle / putText / imwrite of VC-dot:358-395 for every queued sample (annotate.write_annotated:
+        every source frame decoded once, outputs painted and encoded on the device)."""
         from . import annotate
-        from .annotate import MARK_DTYPE
         jobs, self.pending_marks = self.pending_marks, []
-        jobs.sort(key=lambda j: j[0])                        # scene by scene: the source frames stay in the page cache
-        for k0 in range(0, len(jobs), batch):
-            chunk = jobs[k0:k0 + batch]
-            imgs = [annotate.jpeg_decode(open(self.scene_infos.get_image_path(s, i), "rb").read(), self.device) for s, i, _, _ in chunk]
-            same = all(im.shape == imgs[0].shape for im in imgs)
-            groups = [list(range(len(chunk)))] if same else [[k] for k in range(len(chunk))]
-            for g in groups:
-                stack = torch.stack([imgs[k] for k in g]).contiguous()
-                rows = [(n, *m) for n, k in enumerate(g) for m in chunk[k][3]]
-                annotate.draw_marks(stack, np.array(rows, dtype=MARK_DTYPE))
-                for n, k in enumerate(g):
-                    path = os.path.join(image_output_dir, chunk[k][2])
-                    os.makedirs(os.path.dirname(path), exist_ok=True)
-                    with open(path, "wb") as f:
-                        f.write(annotate.jpeg_encode(stack[n]))
-        return len(jobs)
+        return annotate.write_annotated([((s, i), path, marks) for s, i, path, marks in jobs],
+                                        lambda key: open(self.scene_infos.get_image_path(*key), "rb").read(),
+                                        image_output_dir, self.device, workers)
 
     def _dataset_with_images(self, output_dir, split, *a, **k):
         image_output_dir = os.path.join(output_dir, "images")

@@ -148,19 +148,13 @@ def render_dot_images(video, video_id: str, samples, marks, plan, img_output_dir
     """OM-dot:408-425: write ``<frame1>_<point>_annotated.jpg`` (decode on nvJPEG, one filled circle painted by
     msp_draw_marks, encode on nvJPEG) and a plain copy of every second frame.  Returns the number of files written."""
     from . import annotate
-    out_dir = os.path.join(img_output_dir, video_id)
-    os.makedirs(out_dir, exist_ok=True)
-    written = 0
-    for k0 in range(0, len(plan), batch):
-        chunk = plan[k0:k0 + batch]
-        imgs = torch.stack([annotate.jpeg_decode(bytes(video["images_jpeg_bytes"][f]), device) for f, _ in chunk]).contiguous()
-        m = marks[(marks["image"] >= k0) & (marks["image"] < k0 + len(chunk))].copy()
-        m["image"] -= k0
-        annotate.draw_marks(imgs, m)
-        for img, (_, rel) in zip(imgs, chunk):
-            with open(os.path.join(img_output_dir, rel), "wb") as f:
-                f.write(annotate.jpeg_encode(img))
-            written += 1
+    os.makedirs(os.path.join(img_output_dir, video_id), exist_ok=True)
+    per_image = [[] for _ in plan]
+    for m in marks:
+        per_image[int(m["image"])].append((int(m["x"]), int(m["y"]), int(m["radius"]), int(m["glyph"]), int(m["org_x"]),
+                                           int(m["org_y"]), tuple(int(c) for c in m["bgr"]), 0))
+    written = annotate.write_annotated([(f, rel, per_image[k]) for k, (f, rel) in enumerate(plan)],
+                                       lambda f: bytes(video["images_jpeg_bytes"][f]), img_output_dir, device)
     for s in samples:                                        # image 2 is not annotated: the original JPEG stream, verbatim
         path = os.path.join(img_output_dir, s["image"][1])
         if not os.path.exists(path):

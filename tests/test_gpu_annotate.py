@@ -159,3 +159,37 @@ def test_jpeg_roundtrip_through_nvjpeg():
     assert tuple(back[400, 600]) [2] > 200 and back[400, 600][0] < 60          # the red dot survived
     with pytest.raises(Exception):
         jpeg_decode(b"not a jpeg")
+
+
+def test_write_annotated_threads_equal_serial(tmp_path):
+    """annotate.write_annotated: sources decoded once and shared by several outputs; 4 worker threads (own streams, own nvJPEG
+    states) write the same bytes as one thread, and each output carries exactly its own marks."""
+    cv2 = pytest.importorskip("cv2")
+    from multi_spatialmllm_b200.annotate import default_atlas, write_annotated
+    H, W = 240, 320
+    rng = np.random.default_rng(3)
+    sources = {}
+    for k in range(5):
+        ok, enc = cv2.imencode(".jpg", np.full((H, W, 3), 40 * k, np.uint8), [cv2.IMWRITE_JPEG_QUALITY, 90])
+        sources[f"f{k}"] = enc.tobytes()
+    atlas = default_atlas()
+    jobs, where = [], {}
+    for j in range(23):
+        key = f"f{j % 5}"
+        x, y = int(rng.integers(30, W - 60)), int(rng.integers(30, H - 30))
+        marks = [(x, y, 10, -1, 0, 0, (0, 0, 255), 0)]
+        if j % 3 == 0:
+            marks.append((x, y, -1, atlas.index("B"), x + 15, y, (0, 255, 0), 0))
+        if j == 7:
+            marks = []
+        jobs.append((key, f"s{j % 2}/out_{j}.jpg", marks))
+        where[f"s{j % 2}/out_{j}.jpg"] = (x, y, bool(marks))
+    assert write_annotated(jobs, sources.__getitem__, str(tmp_path / "a"), workers=1) == 23
+    assert write_annotated(jobs, sources.__getitem__, str(tmp_path / "b"), workers=4, batch=2) == 23
+    for rel, (x, y, marked) in where.items():
+        a, b = open(tmp_path / "a" / rel, "rb").read(), open(tmp_path / "b" / rel, "rb").read()
+        assert a == b
+        img = cv2.imdecode(np.frombuffer(a, np.uint8), cv2.IMREAD_COLOR)
+        assert img.shape == (H, W, 3)
+        assert (img[y, x, 2] > 200 and img[y, x, 0] < 80) == marked
+    assert write_annotated([], sources.__getitem__, str(tmp_path / "c")) == 0

@@ -183,9 +183,9 @@ def test_pair_engine_matches_reference(run_index, disk, relations, golden, tmp_p
         from multi_spatialmllm_b200.annotate import default_atlas
         flush = eng.flush_images
 
-        def spy(image_output_dir, batch=32):
+        def spy(image_output_dir, *a):
             logged.extend(_marks_as_log(eng.pending_marks, default_atlas()))
-            return flush(image_output_dir, batch)
+            return flush(image_output_dir, *a)
 
         eng.flush_images = spy
     random.seed(run["seed"])
