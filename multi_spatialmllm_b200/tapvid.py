@@ -210,3 +210,154 @@ def generate_split(npz_files, output_file: str, question_type="tapvid3d_total_di
     if max_samples > 0 and len(out) > max_samples:
         out = random.Random(seed).sample(out, max_samples)
     return streams.write_jsonl(out, output_file)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's engine classes (same names, constructor, methods and file layout)
+# ------------------------------------------------------------------------------------------------
+class TwoFrameVideoQAEngine:
+    """single_object_movement_engine_coord.py:281-645.  The reference maps ``generate_qa_training_single_scene`` over a
+    ``multiprocessing.Pool`` (OM-coord:584); here the videos of a call run back to back on this process's GPU — give every
+    rank its share of ``scene_id_list`` (shard.my_shard) to use several GPUs."""
+    dot = False
+
+    def __init__(self, question_type, sub_dataset, templates=None, device="cuda:0"):
+        self.question_type, self.sub_dataset, self.templates, self.device = question_type, sub_dataset, templates, device
+        loose = self.dot and sub_dataset == "drivetrack"                         # OM-dot:301-303
+        self.object_not_moving_threshold = 0.1 if loose else OBJECT_NOT_MOVING_THRESHOLD
+        self.camera_not_moving_threshold = 0.1 if loose else CAMERA_NOT_MOVING_THRESHOLD
+
+    def project_point(self, point_3d, intrinsics, image_height, image_width, id=""):
+        """OM-coord:293-315 through msp_track_project (float64 arithmetic on a float32 track position, which is what the
+        TAPVid-3D files hold): [u_normalized, v_normalized], or None when the point is outside the image or behind."""
+        p = np.asarray(point_3d, dtype=np.float64).reshape(3)
+        p32 = p.astype(np.float32)
+        if not np.array_equal(p32.astype(np.float64), p):
+            raise ValueError("project_point expects a float32 track position (tracks_XYZ); got a float64 value that is not "
+                             "float32-representable")
+        vid = DeviceVideo(p32.reshape(1, 1, 3), np.eye(4)[None], intrinsics, (image_height, image_width), device=self.device)
+        vid.project()
+        if not bool(vid.valid.cpu().numpy()[0, 0]):
+            u, v = vid.uvn.cpu().numpy()[0, 0]
+            print(f"({u}, {v}, {p[2]}) is invaid. Points3D are {point_3d}. intrinsics is {intrinsics}.")
+            return None
+        return [float(x) for x in vid.uvn.cpu().numpy()[0, 0]]
+
+    def generate_qa_training_single_scene(self, input_file, *args, **kwargs):
+        """OM-coord:406 ``(input_file, npoints_per_group=5, npairs_per_bin=1e8, img_output_dir="", augment=True,
+        augment_ratio=1.0)``; the dot engine takes ``base_img_dir`` as second positional argument (OM-dot:448)."""
+        names = (("base_img_dir",) if self.dot else ()) + ("npoints_per_group", "npairs_per_bin", "img_output_dir", "augment", "augment_ratio")
+        a = {"npoints_per_group": 5, "npairs_per_bin": 1e8, "img_output_dir": "", "augment": True, "augment_ratio": 1.0,
+             **dict(zip(names, args)), **kwargs}
+        video_id = os.path.splitext(os.path.basename(input_file))[0]
+        return generate_video_samples(load_video(input_file), video_id, self.question_type, a["npoints_per_group"],
+                                      a["npairs_per_bin"], a["img_output_dir"] or None, None, a["augment"], a["augment_ratio"],
+                                      self.templates, random, self.device, self.dot, self.object_not_moving_threshold,
+                                      self.camera_not_moving_threshold)
+
+    def _all_videos(self, scene_id_list, source_data_root, npoints_per_group, npairs_per_bin, img_output_dir, augment, augment_ratio):
+        data = []
+        for scene_id in scene_id_list:
+            data.extend(self.generate_qa_training_single_scene(os.path.join(source_data_root, f"{scene_id}.npz"),
+                                                               npoints_per_group=npoints_per_group, npairs_per_bin=npairs_per_bin,
+                                                               img_output_dir=img_output_dir, augment=augment, augment_ratio=augment_ratio))
+        return data
+
+    @staticmethod
+    def _report(kind, path, data):
+        still = sum(1 for e in data if e["point_moving"] == 0)
+        cam_still = sum(1 for e in data if e["cam_moving"] == 0)
+        print(f"{kind} data saved to {path}. In total, there are {len(data)} samples.")
+        print(f"Object not moving: {still}, Object moving: {len(data) - still}")
+        print(f"Camera not moving: {cam_still}, Camera moving: {len(data) - cam_still}")
+
+    def generate_qa_training_data(self, scene_id_list, source_data_root, output_dir, output_file, img_output_dir, npoints_per_group,
+                                  npairs_per_bin, augment, augment_ratio=1.0, max_samples=-1, num_workers=20, base_img_dir=None):
+        """OM-coord:580-607 / OM-dot:626-652: all videos, optional random.sample, random.shuffle, JSONL."""
+        data = self._all_videos(scene_id_list, source_data_root, npoints_per_group, npairs_per_bin, img_output_dir, augment, augment_ratio)
+        if max_samples > 0 and len(data) > max_samples:
+            data = random.sample(data, max_samples)
+        random.shuffle(data)
+        streams.write_jsonl(data, output_file)
+        self._report("Training", output_file, data)
+        return data
+
+    @staticmethod
+    def format_eval_sample(training_sample):
+        training_sample["text"] = training_sample["conversations"][0]["value"]
+        return training_sample
+
+    def generate_qa_eval_data(self, scene_id_list, source_data_root, output_dir, output_file, img_output_dir, npoints_per_group,
+                              npairs_per_bin, augment, augment_ratio=0.3, max_samples=300, num_workers=20, base_img_dir=None):
+        """OM-coord:614-644 (sub-sample, then eval format) / OM-dot:659-707 (eval format, ``*_orig.jsonl`` with everything, then
+        the sub-sample; the reference leaves the sub-sample undefined when nothing has to be dropped — all samples here)."""
+        data = self._all_videos(scene_id_list, source_data_root, npoints_per_group, npairs_per_bin, img_output_dir, augment, augment_ratio)
+        if self.dot:
+            data = [self.format_eval_sample(s) for s in data]
+            streams.write_jsonl(data, output_file.replace(".jsonl", "_orig.jsonl"))
+            self._report("Original evaluation", output_file.replace(".jsonl", "_orig.jsonl"), data)
+        if max_samples > 0 and len(data) > max_samples:
+            data = random.sample(data, max_samples)
+        if not self.dot:
+            data = [self.format_eval_sample(s) for s in data]
+        streams.write_jsonl(data, output_file)
+        self._report("Subsampled evaluation" if self.dot else "Evaluation", output_file, data)
+        return data
+
+
+class TwoFrameVideoQAEngineDot(TwoFrameVideoQAEngine):
+    """single_object_movement_engine_dot.py:294-707 (first image annotated on the device, ids ending in ``_ann``)."""
+    dot = True
+
+
+def main(argv=None):
+    """``python -m multi_spatialmllm_b200.tapvid {coord,dot}`` = the ``__main__`` of OM-coord:647-706 / OM-dot:709-779:
+    val then train for both question types over adt and pstudio, the reference's directory and file names."""
+    import argparse
+    import shutil
+    ap = argparse.ArgumentParser()
+    ap.add_argument("variant", choices=["coord", "dot"])
+    ap.add_argument("--base_npz_file", default="data/tapvid3d_dataset")
+    ap.add_argument("--meta_data_dir", default="data/tapvid3d_dataset/meta_data")
+    ap.add_argument("--train_root", default=None)
+    ap.add_argument("--val_root", default=None)
+    ap.add_argument("--img_output_dir", default="data/my_tapvid3d_images")
+    ap.add_argument("--sub_datasets", default="adt,pstudio")
+    ap.add_argument("--version", default="v1_0")
+    ap.add_argument("--reference_root", default=None)
+    ap.add_argument("--seed", type=int, default=None, help="default: what the reference module sets at import")
+    a = ap.parse_args(argv)
+    dot = a.variant == "dot"
+    train_dir = os.path.join(a.train_root or ("training_data_v2/object_movement_dot" if dot else "training_data/object_movement_coord"), a.version)
+    val_dir = os.path.join(a.val_root or ("evaluation_data_v2/object_movement_dot" if dot else "evaluation_data/object_movement_coord"), a.version)
+    tp = streams.Templates.from_reference(a.reference_root) if a.reference_root else None
+    if a.seed is not None:
+        random.seed(a.seed)
+    cls = TwoFrameVideoQAEngineDot if dot else TwoFrameVideoQAEngine
+
+    def ids(sub, split):
+        with open(os.path.join(a.meta_data_dir, sub, f"{split}.txt")) as f:
+            return [ln.rstrip("\n") for ln in f if ln.strip()]
+
+    q_types = ("tapvid3d_total_distance", "tapvid3d_displacement_vector")
+    for split, out_root in (("val", val_dir), ("train", train_dir)):
+        for q_type in q_types:
+            for sub in a.sub_datasets.split(","):
+                out = os.path.join(out_root, sub)
+                os.makedirs(out, exist_ok=True)
+                eng = cls(q_type, sub, templates=tp)
+                src = os.path.join(a.base_npz_file, sub)
+                if split == "val":
+                    img = os.path.join(out, f"{q_type}_images") if dot else a.img_output_dir
+                    if dot and os.path.exists(img):
+                        shutil.rmtree(img)
+                    eng.generate_qa_eval_data(ids(sub, "val"), src, out, os.path.join(out, f"{sub}_{q_type}_val.jsonl"), img, 1, 1,
+                                              augment=False, max_samples=300)
+                else:
+                    img = os.path.join(out, f"{q_type}_images_15points_30pairs") if dot else a.img_output_dir
+                    eng.generate_qa_training_data(ids(sub, "train"), src, out, os.path.join(out, f"{sub}_{q_type}_train_15points_30pairs.jsonl"),
+                                                  img, 15, 30, augment=True, augment_ratio=0.05)
+
+
+if __name__ == "__main__":
+    main()

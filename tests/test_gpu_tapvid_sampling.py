@@ -165,3 +165,65 @@ def test_dot_variant_matches_reference(tmp_path):
         px = img[m0["y"], m0["x"]].astype(int)
         assert np.abs(px - m0["bgr"].astype(int)).sum() < np.abs(np.array([90, 90, 90]) - m0["bgr"].astype(int)).sum() or \
             np.abs(np.array([90, 90, 90]) - m0["bgr"].astype(int)).sum() < 60
+
+
+@pytest.mark.gpu
+def test_reference_named_engine_classes(tmp_path, golden_tapvid):
+    """TwoFrameVideoQAEngine / TwoFrameVideoQAEngineDot: the reference's class surface (constructor, project_point,
+    generate_qa_training_single_scene, generate_qa_training_data / generate_qa_eval_data, __main__ layout)."""
+    import cv2
+    from multi_spatialmllm_b200 import tapvid
+    from oracle import geometry as og
+    g = golden_tapvid
+    eng = tapvid.TwoFrameVideoQAEngine("tapvid3d_total_distance", "adt")
+    H, W = (int(x) for x in g["image_hw"])
+    n_none = 0
+    for t in range(0, g["tracks_xyz"].shape[0], 3):
+        for n in range(0, g["tracks_xyz"].shape[1], 5):
+            want = og.track_project_point(g["tracks_xyz"][t, n], g["fxfycxcy"], H, W)
+            got = eng.project_point(g["tracks_xyz"][t, n], g["fxfycxcy"], H, W)
+            assert got == want                                         # bit-identical floats, or None on both sides
+            n_none += got is None
+    assert eng.project_point(np.array([0.1, 0.1, -1.0], np.float32), g["fxfycxcy"], H, W) is None
+    with pytest.raises(ValueError):
+        eng.project_point([0.1, 0.2, 1.0 / 3.0], g["fxfycxcy"], H, W)
+    # a two-subset dataset on disk in the release layout
+    base, meta = tmp_path / "tapvid3d_dataset", tmp_path / "tapvid3d_dataset" / "meta_data"
+    ok, jpg = cv2.imencode(".jpg", np.full((36, 64, 3), 90, np.uint8))
+    for sub, seeds in (("adt", (31, 32, 33)), ("pstudio", (41, 42))):
+        (base / sub).mkdir(parents=True)
+        (meta / sub).mkdir(parents=True)
+        names = []
+        for seed in seeds:
+            v = _clip(seed, 16, 36, 2)
+            np.savez(str(base / sub / f"{v.video_id}.npz"), images_jpeg_bytes=np.array([jpg.tobytes()] * 16, dtype=object),
+                     fx_fy_cx_cy=v.fxfycxcy, tracks_XYZ=v.tracks_xyz, visibility=v.visibility, extrinsics_w2c=v.w2c)
+            names.append(v.video_id)
+        (meta / sub / "train.txt").write_text("\n".join(names[:-1]) + "\n")
+        (meta / sub / "val.txt").write_text(names[-1] + "\n")
+    one = str(base / "adt" / "video00031.npz")
+    random.seed(3)
+    a = eng.generate_qa_training_single_scene(one, 5, 1e8, "", True, 0.5)
+    random.seed(3)
+    b = tapvid.generate_video_samples(tapvid.load_video(one), "video00031", "tapvid3d_total_distance", 5, 1e8, None, None, True, 0.5)
+    assert a == b and len(a) > 0
+    random.seed(0)
+    eng.generate_qa_training_data(["video00031", "video00032"], str(base / "adt"), str(tmp_path), str(tmp_path / "t.jsonl"),
+                                  str(tmp_path / "img"), 3, 5, True, 0.05, max_samples=40)
+    rows = [json.loads(l) for l in open(tmp_path / "t.jsonl")]
+    assert len(rows) == 40 and os.path.exists(tmp_path / "img" / "video00032" / "00000.jpg")
+    tapvid.main(["coord", "--base_npz_file", str(base), "--meta_data_dir", str(meta), "--train_root", str(tmp_path / "tr"),
+                 "--val_root", str(tmp_path / "va"), "--img_output_dir", str(tmp_path / "img2"), "--seed", "1"])
+    for sub in ("adt", "pstudio"):
+        for q in ("tapvid3d_total_distance", "tapvid3d_displacement_vector"):
+            tr = tmp_path / "tr" / "v1_0" / sub / f"{sub}_{q}_train_15points_30pairs.jsonl"
+            va = tmp_path / "va" / "v1_0" / sub / f"{sub}_{q}_val.jsonl"
+            assert tr.exists() and va.exists()
+            val_rows = [json.loads(l) for l in open(va)]
+            assert val_rows and all("text" in r and r["question_type"] == q for r in val_rows)
+    tapvid.main(["dot", "--base_npz_file", str(base), "--meta_data_dir", str(meta), "--train_root", str(tmp_path / "trd"),
+                 "--val_root", str(tmp_path / "vad"), "--sub_datasets", "pstudio", "--seed", "1"])
+    d = tmp_path / "vad" / "v1_0" / "pstudio"
+    assert (d / "pstudio_tapvid3d_total_distance_val.jsonl").exists() and (d / "pstudio_tapvid3d_total_distance_val_orig.jsonl").exists()
+    row = json.loads(open(d / "pstudio_tapvid3d_total_distance_val.jsonl").readline())
+    assert row["id"].endswith("_ann") and (d / "tapvid3d_total_distance_images" / row["image"][0]).exists()
