@@ -58,7 +58,7 @@ def process_visibility_split(split_name, scene_info_path, visibility_parquet_fil
     with open(os.path.join(output_dir, "warning.txt"), "w") as wf:
         wf.write("")
     out = tables.run_object_visibility_split(_handler(scene_info_path), os.path.join(output_dir, "object_visibility.pkl"),
-                                             device=device)
+                                             device=device, warning_file=os.path.join(output_dir, "warning.txt"))
     print(f"Finished processing split '{split_name}'.")
     return out
 

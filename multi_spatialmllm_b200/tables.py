@@ -229,7 +229,19 @@ class _ParquetStream:
         return self.rows
 
 
-def run_visibility_split(scene_infos, output_file: str, scene_ids=None, device="cuda:0") -> dict:
+def _warn_empty_frames(sc, scene_id, image_ids, warning_file, text):
+    """MVI:110-113 / CFR:159-161: one line per valid frame that sees no point."""
+    if not warning_file:
+        return
+    valid = sc.valid.cpu().numpy().astype(bool)
+    seen = sc.mask.ne(0).any(dim=1).cpu().numpy()
+    lines = [text.format(scene_id=scene_id, image_id=i) for f, i in enumerate(image_ids) if valid[f] and not seen[f]]
+    if lines:
+        with open(warning_file, "a") as f:
+            f.writelines(lines)
+
+
+def run_visibility_split(scene_infos, output_file: str, scene_ids=None, device="cuda:0", warning_file=None) -> dict:
     """make_visibility_info.run_split + convert_pkl_to_parquet (MVI:127-177, 38-73) on the GPU: streams one row group
     per scene into the canonical parquet (same keys, same JSON text, same row order as the reference's file)."""
     out = _ParquetStream(output_file)
@@ -237,11 +249,12 @@ def run_visibility_split(scene_infos, output_file: str, scene_ids=None, device="
     for sid in (scene_ids if scene_ids is not None else scene_infos.get_all_scene_ids()):
         sc, image_ids = device_scene_from_handler(scene_infos, sid, device)
         out.write(visibility_arrow_table(sc, sid, image_ids))
+        _warn_empty_frames(sc, sid, image_ids, warning_file, "[Warning] {scene_id}: {image_id} has no in-bound points.\n")
         n_scenes += 1
     return {"scenes": n_scenes, "rows": out.close(), "file": output_file}
 
 
-def run_relations_split(scene_infos, output_parquet: str, scene_ids=None, device="cuda:0") -> dict:
+def run_relations_split(scene_infos, output_parquet: str, scene_ids=None, device="cuda:0", warning_file=None) -> dict:
     """calculate_frames_relations.run_split (CFR:200-253) on the GPU: <file> and <file>_nonzero.parquet (CFR:59-84;
     NaN != 0.0, so pairs with an empty union stay in the nonzero table like in the reference)."""
     import pyarrow.compute as pc
@@ -252,15 +265,25 @@ def run_relations_split(scene_infos, output_parquet: str, scene_ids=None, device
         sc, image_ids = device_scene_from_handler(scene_infos, sid, device)
         t = relations_arrow_table(sc, sid, image_ids)
         full.write(t)
+        _warn_empty_frames(sc, sid, image_ids, warning_file, "{scene_id}: {image_id} has no in bound points\n")
         if t.num_rows:
             ov = t["overlap"]
             nonzero.write(t.filter(pc.or_(pc.is_nan(ov), pc.not_equal(ov, 0.0))))
+            if warning_file:                                                      # CFR:191-194: rows holding NaN / inf
+                bad = t.filter(pc.invert(pc.and_(pc.and_(pc.is_finite(t["overlap"]), pc.is_finite(t["distance"])),
+                                                 pc.and_(pc.is_finite(t["yaw"]), pc.is_finite(t["pitch"]))))).to_pylist()
+                if bad:
+                    with open(warning_file, "a") as f:
+                        for r in bad:
+                            vals = [np.float64(r[k]) for k in ("overlap", "distance", "yaw", "pitch")]
+                            f.write(f"{sid}: {(r['image_id1'], r['image_id2'])} has something wrong {vals}. \n")
         n_scenes += 1
     return {"scenes": n_scenes, "rows": full.close(), "rows_nonzero": nonzero.close(), "file": output_parquet}
 
 
-def object_visibility_scene(scene_infos, scene_id: str, sc: "engine.DeviceScene", image_ids) -> dict:
-    """compute_object_visibility.process_scene (COV:72-152) from the device's per-(frame, object) counts."""
+def object_visibility_scene(scene_infos, scene_id: str, sc: "engine.DeviceScene", image_ids, warnings_list=None) -> dict:
+    """compute_object_visibility.process_scene (COV:72-152) from the device's per-(frame, object) counts; the reference's
+    warning lines (objects without points, COV:112-116) are appended to ``warnings_list`` when given."""
     result = {"object_to_images": {}, "image_to_objects": {}}
     sc.project_visibility()
     counts = sc.object_counts().cpu().numpy()
@@ -271,6 +294,9 @@ def object_visibility_scene(scene_infos, scene_id: str, sc: "engine.DeviceScene"
             continue
         total = int(np.count_nonzero(inst == o + 1))
         if total == 0:
+            if warnings_list is not None:
+                warnings_list.append(f"[Warning] Scene {scene_id}, object {o} has no point indices, skipping.")
+                print(warnings_list[-1])
             continue
         thr = max(1, int(0.05 * total))
         for f, image_id in enumerate(image_ids):
@@ -282,11 +308,15 @@ def object_visibility_scene(scene_infos, scene_id: str, sc: "engine.DeviceScene"
     return result
 
 
-def run_object_visibility_split(scene_infos, output_pkl: str, scene_ids=None, device="cuda:0") -> dict:
-    out = {}
+def run_object_visibility_split(scene_infos, output_pkl: str, scene_ids=None, device="cuda:0", warning_file=None) -> dict:
+    """compute_object_visibility.process_split (COV:154-194): {scene: result} pickled to ``output_pkl``."""
+    out, warnings_list = {}, []
     for sid in (scene_ids if scene_ids is not None else scene_infos.get_all_scene_ids()):
         sc, image_ids = device_scene_from_handler(scene_infos, sid, device)
-        out[sid] = object_visibility_scene(scene_infos, sid, sc, image_ids)
+        out[sid] = object_visibility_scene(scene_infos, sid, sc, image_ids, warnings_list)
+    if warning_file:
+        with open(warning_file, "a") as wf:
+            wf.writelines(w + "\n" for w in warnings_list)
     os.makedirs(os.path.dirname(output_pkl) or ".", exist_ok=True)
     with open(output_pkl, "wb") as f:
         pickle.dump(out, f)
@@ -395,13 +425,18 @@ def main(argv=None):
         out = getattr(a, f"{split}_output") or L2_DEFAULTS[a.table][split]
         os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
         scene_ids = h.get_all_scene_ids()
+        warn = os.path.join(os.path.dirname(out) or ".", {"visibility": f"make_visibility_{split}_warning.txt",      # MVI:200-201
+                                                          "relations": f"{split}_warning_D5.txt",                    # CFR:270-271
+                                                          "object_visibility": "warning.txt"}[a.table])              # COV:166
+        if rank > 0:
+            warn = shard.part_path(warn, rank)
         if world == 1:
-            results[split] = run(h, out, device=device)
+            results[split] = run(h, out, device=device, warning_file=warn)
             continue
         costs = {s: shard.scene_cost(len(h.get_scene_points_align(s)), h.get_num_posed_images(s)) for s in scene_ids}
         mine = set(shard.my_shard(costs, rank, world))
         part = shard.part_path(out, rank)
-        res = run(h, part, scene_ids=[s for s in scene_ids if s in mine], device=device)
+        res = run(h, part, scene_ids=[s for s in scene_ids if s in mine], device=device, warning_file=warn)
         man = shard.gather_manifest({"rank": rank, "part": part, "scenes": len(mine)})
         if rank == 0:
             parts = [m["part"] for m in man]

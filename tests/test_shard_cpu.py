@@ -114,7 +114,7 @@ def test_two_rank_tables_cli_gloo(tmp_path):
         import pyarrow as pa
         from multi_spatialmllm_b200 import tables
 
-        def fake_relations(h, output_parquet, scene_ids=None, device="cuda:0"):
+        def fake_relations(h, output_parquet, scene_ids=None, device="cuda:0", warning_file=None):
             full = tables._ParquetStream(output_parquet)
             nz = tables._ParquetStream(output_parquet.replace(".parquet", "_nonzero.parquet"))
             for s in scene_ids:
