@@ -133,7 +133,7 @@ def test_compute_object_visibility_process_scene(disk, golden, tmp_path):
     assert "1" not in g["result"]["object_to_images"]                         # the wall is skipped (COV:58)
     _, empty, w = cov.process_scene("scene9999_00", h, {})
     assert empty == {"object_to_images": {}, "image_to_objects": {}} and "not found" in w[0]
-    cov.process_split("val", info, None, str(tmp_path / "op"))
+    cov.process_split("val", h, None, str(tmp_path / "op"))
     import pickle
     with open(tmp_path / "op" / "object_visibility.pkl", "rb") as f:
         assert json.loads(json.dumps(pickle.load(f)[sid])) == g["result"]
