@@ -190,7 +190,8 @@ class DeviceScene:
 
     # ---- pair stage ----------------------------------------------------------------------------
     def pair_overlap(self, pairs):
-        pairs_d = _to_device(np.asarray(pairs, dtype=np.int32).reshape(-1, 2), torch.int32, self.device)
+        pairs_d = _to_device(pairs if isinstance(pairs, torch.Tensor) else np.asarray(pairs, dtype=np.int32).reshape(-1, 2),
+                             torch.int32, self.device)
         P = int(pairs_d.shape[0])
         inter = torch.empty((P,), dtype=torch.int32, device=self.device)
         uni = torch.empty((P,), dtype=torch.int32, device=self.device)
