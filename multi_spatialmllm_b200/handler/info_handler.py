@@ -193,11 +193,13 @@ class SceneInfoHandler:
 
     def get_depth_image(self, scene_id, image_id):
         key = (scene_id, self.convert_image_id_to_key(image_id))
-        if key not in self._depth_cache:
+        d = self._depth_cache.get(key)
+        if d is None:                                        # called from decoder threads too: never index after a clear()
+            d = cv2.imread(self.get_depth_image_path(scene_id, image_id), -1)
             if len(self._depth_cache) > 256:
                 self._depth_cache.clear()
-            self._depth_cache[key] = cv2.imread(self.get_depth_image_path(scene_id, image_id), -1)
-        return self._depth_cache[key]
+            self._depth_cache[key] = d
+        return d
 
     # ---- objects --------------------------------------------------------------------------------
     def get_object_gt_bbox(self, scene_id, object_id, axis_aligned=True, with_class_id=False):

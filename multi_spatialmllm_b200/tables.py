@@ -71,8 +71,13 @@ def device_scene_from_handler(scene_infos, scene_id: str, device="cuda:0"):
     c2w = np.stack([scene_infos.get_extrinsic_matrix(scene_id, i, warning=False) for i in image_ids])
     H, W = scene_infos.get_image_shape(scene_id)
     depth = None
-    for f, i in enumerate(image_ids):
-        d = scene_infos.get_depth_image(scene_id, i)
+    if len(image_ids) > 8:                                   # cv2.imread releases the GIL: decode the PNGs on a few threads
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as pool:
+            maps = list(pool.map(lambda i: scene_infos.get_depth_image(scene_id, i), image_ids))
+    else:
+        maps = [scene_infos.get_depth_image(scene_id, i) for i in image_ids]
+    for f, d in enumerate(maps):
         if d is None:
             continue
         if depth is None:
