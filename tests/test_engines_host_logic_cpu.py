@@ -1,0 +1,214 @@
+"""Host logic of the drop-in QA engines on CPU: the engines run unchanged, the device layer underneath them (DeviceScene's
+pair_overlap / pair_annotate, SceneSession's per-frame tables) is replaced by a stand-in that answers the same requests
+from the NumPy oracle.  What is checked is everything above the C ABI — row grouping, the speculative replay of Python's
+RNG stream, sampling, formatting — against the goldens of the unmodified reference engines
+(tests/golden/make_golden_pair_engines.py, make_golden_depth_engines.py).  The kernels' side of the same goldens is the
+`-m gpu` suite (tests/test_pair_engines.py, tests/test_gpu_engines.py)."""
+import gzip
+import importlib.util
+import json
+import os
+import random
+from itertools import combinations
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from multi_spatialmllm_b200 import synth
+from multi_spatialmllm_b200.engine import PAIR_RECORD_DTYPE
+from oracle import geometry as og
+from oracle import ref_layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleScene:
+    """Answers DeviceScene's pair requests from the oracle (float64 NumPy, the reference's own arithmetic)."""
+
+    def __init__(self, s):
+        self.s, self.pts = s, s.points.astype(np.float64)
+        self.H, self.W = s.image_hw
+        self.valid = [bool(np.isfinite(s.c2w[f]).all()) for f in range(s.n_frames)]
+        self.E = [og.aligned_pose(s.axis_align, s.c2w[f]) if self.valid[f] else None for f in range(s.n_frames)]
+        with np.errstate(all="ignore"):
+            self.masks = [og.frame_visibility(self.pts, s.K, self.E[f], s.depth[f], self.H, self.W)[2] if self.valid[f]
+                          else np.zeros(len(self.pts), bool) for f in range(s.n_frames)]
+
+    def pair_overlap(self, pairs):
+        pairs = np.asarray(pairs).reshape(-1, 2)
+        inter = np.array([int((self.masks[a] & self.masks[b]).sum()) for a, b in pairs], np.int32)
+        uni = np.array([int((self.masks[a] | self.masks[b]).sum()) for a, b in pairs], np.int32)
+        with np.errstate(all="ignore"):
+            return torch.from_numpy(inter), torch.from_numpy(uni), torch.from_numpy(inter / uni * 100.0)
+
+    def pair_annotate(self, pairs, sel, sel_mode=0, out=None):
+        assert sel_mode == 0
+        rec = np.zeros(len(pairs), PAIR_RECORD_DTYPE)
+        for r, ((a, b), k) in zip(rec, zip(np.asarray(pairs).tolist(), np.asarray(sel).tolist())):
+            common = np.flatnonzero(self.masks[a] & self.masks[b])
+            r["inter"], r["uni"] = len(common), int((self.masks[a] | self.masks[b]).sum())
+            rel = og.pair_relations(self.E[a], self.E[b], self.masks[a], self.masks[b])
+            r["overlap"], r["distance"], r["dyaw"], r["dpitch"] = rel["overlap"], rel["distance"], rel["yaw"], rel["pitch"]
+            r["rel_disp"] = og.relative_displacement(self.E[a], self.E[b])[0]
+            r["point_id"] = common[k] if k < len(common) else -1
+            if r["point_id"] >= 0:
+                for slot, f in enumerate((a, b)):
+                    an = og.annotate_point(self.pts[r["point_id"]], self.s.K, self.E[f], self.s.depth[f], self.H, self.W)
+                    if an is not None:
+                        r["flags"] |= 1 << slot
+                        r["permille"][2 * slot:2 * slot + 2] = (an["x_permille"], an["y_permille"])
+                        r["depth_mm"][slot] = an["depth_mm"]
+                        r["pix"][2 * slot:2 * slot + 2] = an["pix"]
+        return rec
+
+    @staticmethod
+    def records_to_numpy(rec):
+        return rec
+
+
+class OracleCache:
+    def __init__(self, scenes):
+        self.scenes = {s.scene_id: (OracleScene(s), {i: f for f, i in enumerate(s.image_ids)}) for s in scenes}
+
+    def get(self, scene_id):
+        return self.scenes[scene_id]
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def pair_setup(tmp_path_factory):
+    from multi_spatialmllm_b200.handler.info_handler import SceneInfoHandler
+    gen = _load(os.path.join(ROOT, "tests", "golden", "make_golden_pair_engines.py"), "_golden_pair_engines_cpu")
+    scenes = gen.scenes()
+    base = tmp_path_factory.mktemp("pair_engines_cpu")
+    root = str(base / "data" / "scannet")
+    info = ref_layout.write_split(scenes, root, name="scenes_train_val_info_i_D5.pkl")
+    h = SceneInfoHandler(info, posed_images_root=os.path.join(root, "posed_images"),
+                         instance_data_root=os.path.join(root, "scannet_instance_data"))
+    cache = OracleCache(scenes)
+    rows = []
+    for s in scenes:                                               # the relations table, CFR:139-197 order
+        sc, _ = cache.get(s.scene_id)
+        valid = [f for f in range(s.n_frames) if sc.valid[f]]
+        for a, b in combinations(valid, 2):
+            with np.errstate(all="ignore"):
+                rel = og.pair_relations(sc.E[a], sc.E[b], sc.masks[a], sc.masks[b])
+            rows.append({"scene_id": s.scene_id, "image_id1": s.image_ids[a], "image_id2": s.image_ids[b], **rel})
+    parquet = str(base / "camera_info_D5.parquet")
+    pd.DataFrame(rows).to_parquet(parquet, index=False)
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "pair_engines.json.gz"), "rt") as f:
+        golden = json.load(f)
+    return h, cache, parquet, golden
+
+
+@pytest.mark.parametrize("run_index", range(7))
+def test_pair_engine_host_logic_matches_reference_cpu(run_index, pair_setup, tmp_path):
+    from multi_spatialmllm_b200 import pair_engines
+    from multi_spatialmllm_b200.annotate import default_atlas
+    h, cache, parquet, golden = pair_setup
+    run = golden["runs"][run_index]
+    cls = {"camera_movement": pair_engines.CameraMovementEngine, "visual_correspondence": pair_engines.VisualCorrespondenceCoorEngine,
+           "visual_correspondence_dot": pair_engines.VisualCorrespondenceDotEngine}[run["engine"]]
+    eng = cls(h, templates=golden["templates"][run["engine"]], rnd=random, cache=cache)
+    logged = []
+    if run["engine"] == "visual_correspondence_dot":
+        def log_only(image_output_dir, *a):                        # painting / JPEG are device work: keep the draw calls only
+            atlas = default_atlas()
+            for _, _, _, marks in eng.pending_marks:
+                for (x, y, r, glyph, ox, oy, color, _) in marks:
+                    logged.append(["circle", x, y, r, list(color), -1])
+                    if glyph >= 0:
+                        logged.append(["text", atlas.chars[glyph], ox, oy, 0, 1.0, list(color), 2])
+            eng.pending_marks = []
+        eng.flush_images = log_only
+    kwargs = dict(run["kwargs"])
+    if run["engine"] != "camera_movement":
+        kwargs["warning_file"] = str(tmp_path / "warn.txt")
+    od = str(tmp_path / "out")
+    os.makedirs(od)
+    random.seed(run["seed"])
+    np.random.seed(run["seed"])
+    getattr(eng, run["fn"])(parquet_path=parquet, output_dir=od, overlap_min=golden["bins"][0], overlap_max=golden["bins"][1],
+                            interval=golden["bins"][2], **kwargs)
+    after, np_after = random.random(), float(np.random.random())
+    got = [json.loads(l) for l in open(os.path.join(od, run["file"]))]
+    assert [s["id"] for s in got] == [s["id"] for s in run["samples"]]
+    assert got == run["samples"]
+    assert after == run["random_after"] and np_after == run["np_random_after"]
+    assert logged == run["draw_log"] and eng.replans == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# depth engines: SceneSession replaced by an oracle-backed session
+# ------------------------------------------------------------------------------------------------
+class OracleSession:
+    def __init__(self, scene_info, scene_id, device=None):
+        self.scene_id = scene_id
+        s = OracleSession.scenes[scene_id]
+        self.sc, self.row = OracleScene(s), {i: f for f, i in enumerate(s.image_ids)}
+
+    def visible_points(self, image_id):
+        from multi_spatialmllm_b200.engines import _IntSeq
+        return _IntSeq(np.flatnonzero(self.sc.masks[self.row[image_id]]))
+
+    def lookup(self, image_id, point):
+        f, sc = self.row[image_id], self.sc
+        an = og.annotate_point(sc.pts[point], sc.s.K, sc.E[f], sc.s.depth[f], sc.H, sc.W)
+        if an is None:
+            return (False, 0, 0, 0, (0, 0))
+        return (True, an["x_permille"], an["y_permille"], an["depth_mm"], an["pix"])
+
+
+@pytest.mark.parametrize("run_index", range(6))
+def test_depth_engine_host_logic_matches_reference_cpu(run_index, golden_scannet, tmp_path, monkeypatch):
+    from multi_spatialmllm_b200 import engines
+    from multi_spatialmllm_b200.annotate import default_atlas
+    g = golden_scannet
+    ids = [str(v) for v in g["image_ids"]]
+    a = synth.SynthScene("scene0011_00", g["points"], g["instance_ids"], int(g["num_objects"]), g["axis_align"], g["c2w"],
+                         g["K"], tuple(int(v) for v in g["image_hw"]), tuple(int(v) for v in g["depth_hw"]),
+                         depth=g["depth"], image_ids=ids)
+    keep = [0, 2, 3, 4, 6]
+    b = synth.SynthScene("scene0012_00", g["points"], g["instance_ids"], int(g["num_objects"]), g["axis_align"], g["c2w"][keep],
+                         g["K"], a.image_hw, a.depth_hw, depth=g["depth"][keep], image_ids=[ids[k] for k in keep])
+    root = str(tmp_path / "data" / "scannet")
+    info = ref_layout.write_split([a, b], root, name="scenes_val_info_i_D5.pkl")
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "depth_engines.json.gz"), "rt") as f:
+        golden = json.load(f)
+    run = golden["runs"][run_index]
+    key, cls_name, n_max, npp, seed, mode = run["run"]
+    OracleSession.scenes = {a.scene_id: a, b.scene_id: b}
+    monkeypatch.setattr(engines, "SceneSession", OracleSession)
+    eng = getattr(engines, cls_name)(info, "v1_0", n_max, str(tmp_path / "images"), None, npp, str(tmp_path / "warn.txt"),
+                                     posed_images_root=os.path.join(root, "posed_images"),
+                                     instance_data_root=os.path.join(root, "scannet_instance_data"),
+                                     templates=golden["templates"][key], rnd=random)
+    logged = []
+
+    def log_only(scene_id):
+        atlas = default_atlas()
+        for _, _, marks in eng.pending_marks:
+            for (x, y, r, glyph, ox, oy, color, _) in marks:
+                logged.append(["circle", x, y, r, list(color), -1])
+                if glyph >= 0:
+                    logged.append(["text", atlas.chars[glyph], ox, oy, 0, 1.0, list(color), 2])
+        eng.pending_marks = []
+
+    eng._flush_images = log_only
+    random.seed(seed)
+    with np.errstate(all="ignore"):
+        if mode == "train":
+            data = eng.generate_qa_training_data(str(tmp_path / "out"), save_file=False)
+        else:
+            eng.generate_qa_eval_data(str(tmp_path / "out"))
+            data = [json.loads(l) for l in open(tmp_path / "out" / f"{eng.task_name}.jsonl")]
+    assert json.loads(json.dumps(data)) == run["samples"]
+    assert random.random() == run["random_after"] and logged == run["draw_log"]
