@@ -212,3 +212,39 @@ def test_depth_engine_host_logic_matches_reference_cpu(run_index, golden_scannet
             data = [json.loads(l) for l in open(tmp_path / "out" / f"{eng.task_name}.jsonl")]
     assert json.loads(json.dumps(data)) == run["samples"]
     assert random.random() == run["random_after"] and logged == run["draw_log"]
+
+
+@pytest.mark.parametrize("name", ["visual_correspondence", "visual_correspondence_dot"])
+def test_speculative_replay_equals_row_by_row_cpu(name, pair_setup):
+    """Device answers that contradict the dry run's prediction (failed re-check; a distractor on the correct pixel): planning
+    every row at once must give what planning one row at a time gives (the reference's sequential order by construction)."""
+    from multi_spatialmllm_b200 import pair_engines
+    h, cache, parquet, golden = pair_setup
+    df = pair_engines.sample_dataframe(pd.read_parquet(parquet), 10 ** 6, 0, 6, 35, 1)
+    cls = pair_engines.VisualCorrespondenceCoorEngine if name == "visual_correspondence" else pair_engines.VisualCorrespondenceDotEngine
+    outs = []
+    for plan_rows in (1 << 18, 1):
+        eng = cls(h, templates=golden["templates"][name], cache=cache)
+        real = eng._device_answers
+
+        def corrupt(ctx, plan, first, real=real):
+            ans = real(ctx, plan, first)
+            for r, a in enumerate(ans, start=first):
+                for rec in a or ():
+                    if name == "visual_correspondence" and r % 11 == 3:
+                        rec["flags"] = 1
+                    if name == "visual_correspondence_dot" and r % 7 == 2:
+                        rec["flags"] = 2 if r % 14 == 2 else 3
+                        rec["pix"][2:] = (5, 5)
+            return ans
+
+        eng._device_answers = corrupt
+        rnd = random.Random(77)
+        if name == "visual_correspondence_dot":
+            real_randint = rnd.randint
+            rnd.randint = lambda a, b, real_randint=real_randint: 5 if (b > 255 and real_randint(0, 3) == 0) else real_randint(a, b)
+        eng.rnd = rnd
+        samples = eng.build_samples(df, None, plan_rows=plan_rows, max_points_per_pair=1)
+        outs.append((json.loads(json.dumps(samples)), rnd.random(), eng.replans))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert outs[0][2] > 3 and any(s is None for s in outs[0][0]) and any(s is not None for s in outs[0][0])
