@@ -47,6 +47,9 @@ constexpr int kCullMaxObjects = 63;
 #ifndef MSP_CULL_PREFETCH
 #define MSP_CULL_PREFETCH 0  // 1: each CTA prefetches its share of the chunk's depth maps into L2 while it sets up (measured: no gain, profiles/tuning_r1.md)
 #endif
+#ifndef MSP_ZBUF_WARP_MIN
+#define MSP_ZBUF_WARP_MIN 0  // K2, 1: warp-level nearest-z agreement per depth pixel (MATCH.ANY + REDUX.MIN) before the global atomicMin (measured slower: profiles/tuning_r1.md)
+#endif
 #ifndef MSP_CULL_W_SMEM
 #define MSP_CULL_W_SMEM 0  // 1: keep the chunk's float64 poses in SMEM for the exact path, 0: read them from global
 #endif  // fused object counting keeps a (64 frames x 64 ids) histogram in SMEM
@@ -388,6 +391,22 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     if (MODE == 1) {
       // z-buffer splat: the pixel is certain, the stored value must be float32(z_ref) — recompute z alone in float64
       // from the original coordinates (IH:60,63 operation order) and splat; nothing is left to compare later
+#if MSP_ZBUF_WARP_MIN
+      // lanes of the warp that hit the same depth pixel first agree on their nearest z (positive floats order like their
+      // bit patterns): MATCH.ANY groups them by pixel, REDUX.MIN reduces inside each group, and only the lanes holding the
+      // group's minimum touch memory - one atomic per (warp, pixel) instead of one per point
+      const uint32_t act = __ballot_sync(0xffffffffu, r.go);
+      if (r.go) {
+        const int idx = warp * kCullWarpPoints + j * 32 + lane;
+        double x64, y64, z64;
+        PtTraits<DT>::load(p.pts, base + idx, x64, y64, z64);
+        const uint32_t zb = __float_as_uint(__double2float_rn(row_dot_h(wz, x64, y64, z64)));
+        const uint32_t peers = __match_any_sync(act, (int)di);
+        uint32_t zmin = zb;
+        if (peers & (peers - 1u)) zmin = __reduce_min_sync(peers, zb);   // uniform within a group of peers
+        if (zb == zmin) atomicMin(zrow + (int)di, zb);
+      }
+#else
       if (r.go) {
         const int idx = warp * kCullWarpPoints + j * 32 + lane;
         double x64, y64, z64;
@@ -395,6 +414,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
         const double zref = row_dot_h(wz, x64, y64, z64);
         atomicMin(zrow + (int)di, __float_as_uint(__double2float_rn(zref)));
       }
+#endif
       r.go = false;
       return r;
     }
