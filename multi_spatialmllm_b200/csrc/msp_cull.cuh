@@ -47,6 +47,12 @@ constexpr int kCullMaxObjects = 63;
 #ifndef MSP_CULL_PREFETCH
 #define MSP_CULL_PREFETCH 0  // 1: each CTA prefetches its share of the chunk's depth maps into L2 while it sets up (measured: no gain, profiles/tuning_r1.md)
 #endif
+#ifndef MSP_CULL_MAGIC_RINT
+#define MSP_CULL_MAGIC_RINT 1  // 1: rint(t) as (t + 1.5*2^23) - 1.5*2^23 on the FMA pipe instead of FRND on the XU pipe (exact for |t| < 2^22)
+#endif
+#ifndef MSP_CULL_MAGIC_I2F
+#define MSP_CULL_MAGIC_I2F 1   // 1: float(raw u16) as as_float(0x4B000000 | raw) - 2^23 instead of I2F on the XU pipe (exact)
+#endif
 #ifndef MSP_ZBUF_WARP_MIN
 #define MSP_ZBUF_WARP_MIN 0  // K2, 1: warp-level nearest-z agreement per depth pixel (MATCH.ANY + REDUX.MIN) before the global atomicMin (measured slower: profiles/tuning_r1.md)
 #endif
@@ -62,8 +68,10 @@ struct CullFrameConsts {  // per (CTA tile, frame); 128 bytes, all relative to t
   float ct1, ct0;         // pixel-index guard band  dt = ct1 * rcp(Z) + ct0
   int std_frame;          // bottom row of w2c is exactly [0,0,0,1]
   int tile_cand;          // 0: the whole 2048-point tile is certainly outside this frame's image
-  int pad[6];
+  unsigned long long dm_biased;  // this frame's depth map as a byte address minus 2 * 0x4B000000 (see eval32's gather)
+  int pad[4];
 };
+static_assert(sizeof(CullFrameConsts) == 128, "CullFrameConsts layout");
 
 struct CullParams {
   const void* pts;
@@ -346,8 +354,9 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       for (int q = 0; q < 4; ++q) c.box[q][0] = c.box[q][1] = c.box[q][2] = c.box[q][3] = 0.f;
       c.B = finf;
     }
+    c.dm_biased = (unsigned long long)(p.depth + (int64_t)(f0 + tid) * p.depth_stride) - 2ull * 0x4B000000ull;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) c.pad[i] = 0;
+    for (int i = 0; i < 4; ++i) c.pad[i] = 0;
     s_c[tid] = c;
   }
   __syncthreads();
@@ -356,7 +365,10 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   const uint32_t lt = (1u << lane) - 1u;
   const bool word_ok = (lane < kCullPtsPerLane) && (word0 + lane < p.mask_stride);
   uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;
-  const float* s_lane = s_rel + 3 * (warp * kCullWarpPoints + lane);  // this lane's point of group j is at s_lane + 96 j
+  // this lane's point of group j is at shared address s_lane + 384 j; the address is made opaque so that it is kept in a
+  // register instead of being re-derived from the thread id at every use (8 instructions per point at 64 registers)
+  uint32_t s_lane = (uint32_t)__cvta_generic_to_shared(s_rel + 3 * (warp * kCullWarpPoints + lane));
+  asm volatile("" : "+r"(s_lane));
   unsigned int st_f32 = 0, st_exact = 0;
 
   // float32 evaluation of one group's point on this lane (branch-free; see the header comment for the bounds)
@@ -368,9 +380,14 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   const double* wz = nullptr;      // MODE 1: row 2 of the current frame's w2c (float64) and its z-buffer row
   unsigned int* zrow = nullptr;
   auto eval32 = [&](int j, const float4& a0, const float4& a2, const float4& az, float B, float B2, float ct1,
-                    float half_ct0, const uint16_t* dm) -> Lane32 {
-    const float* q = s_lane + 96 * j;
-    const float x = q[0], y = q[1], z = q[2];
+                    float half_ct0, unsigned long long dmb) -> Lane32 {
+    float x, y, z;
+    {
+      const uint32_t q = s_lane + 384u * (uint32_t)j;
+      asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(q));
+      asm("ld.shared.f32 %0, [%1+4];" : "=f"(y) : "r"(q));
+      asm("ld.shared.f32 %0, [%1+8];" : "=f"(z) : "r"(q));
+    }
     const float I0 = fmaf(a0.x, x, fmaf(a0.y, y, fmaf(a0.z, z, a0.w)));
     const float I1 = fmaf(a2.x, x, fmaf(a2.y, y, fmaf(a2.z, z, a2.w)));
     const float Z = fmaf(az.x, x, fmaf(az.y, y, fmaf(az.z, z, az.w)));
@@ -379,7 +396,11 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     const bool cin = m >= B2;                               // certainly inside the image, in front of the camera
     const float rz = rcp_approx(Z);
     const float tx = I0 * rz, ty = I1 * rz;
+#if MSP_CULL_MAGIC_RINT
+    const float ix = (tx + 12582912.0f) - 12582912.0f, iy = (ty + 12582912.0f) - 12582912.0f;  // = rintf for |t| < 2^22; lanes beyond are never `go`
+#else
     const float ix = rintf(tx), iy = rintf(ty);
+#endif
     const float e = fmaxf(fabsf(tx - ix), fabsf(ty - iy));
     const bool pc = e <= fmaf(-ct1, rz, half_ct0);          // the reference rounds to the same depth pixel
     const float di = fmaf(fminf(iy, p.fdh1), p.fdw, fminf(ix, p.fdw1));
@@ -418,17 +439,24 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       r.go = false;
       return r;
     }
+    // di is an exact integer below 2^23 on every lane that gathers: adding 2^23 leaves it in the low mantissa bits
+    // (0x4B000000 + di), and dm_biased already subtracts that constant - no float->int conversion on the XU pipe
+    const uint32_t dbits = __float_as_uint(di + 8388608.0f);
 #if defined(MSP_EXPERIMENT_NO_GATHER)
     if (r.go) r.raw = 60000u;                                   // upper bound experiment: no memory access
 #elif defined(MSP_EXPERIMENT_HOT_GATHER)
-    if (r.go) r.raw = ldg_u16_nc(dm + ((int)di & 4095)) | 0x8000u;  // upper bound experiment: always-cached gather
+    if (r.go) r.raw = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dmb + 2ull * (0x4B000000u + (dbits & 4095u)))) | 0x8000u;
 #else
-    if (r.go) r.raw = ldg_u16_nc(dm + (int)di);
+    if (r.go) r.raw = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dmb + 2ull * dbits));
 #endif
     return r;
   };
   auto cmp32 = [&](const Lane32& r, float Bz, bool& vis, bool& unc) {
+#if MSP_CULL_MAGIC_I2F
+    const float d = (__uint_as_float(0x4B000000u | r.raw) - 8388608.0f) * p.fscale;
+#else
     const float d = (float)r.raw * p.fscale;
+#endif
     const float mz = fmaf(3.6e-7f, d, Bz);  // 6u d + B_Z: d^ is within 2.1u d of raw*0.001, plus the rounding of z^ - d^
     const float t = r.zf - d;
     vis = r.go && (t < -mz);
@@ -472,7 +500,8 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       const float4 a2 = *reinterpret_cast<const float4*>(c.box[2]);
       const float4 az = *reinterpret_cast<const float4*>(c.fz);
       const float B2 = B + B, ct1 = c.ct1, half_ct0 = 0.5f - c.ct0, Bz = c.Bz;
-      const uint16_t* dm = p.depth + f * p.depth_stride;
+      unsigned long long dm = c.dm_biased;
+      asm volatile("" : "+l"(dm));  // keep the frame's depth base in registers (it is otherwise rebuilt per gather)
       if (MODE == 1) {
         wz = s_w + fi * 16 + 8;
         zrow = reinterpret_cast<unsigned int*>(p.zbuf + f * p.depth_stride);
