@@ -47,6 +47,15 @@ constexpr int kCullMaxObjects = 63;
 #ifndef MSP_CULL_PREFETCH
 #define MSP_CULL_PREFETCH 0  // 1: each CTA prefetches its share of the chunk's depth maps into L2 while it sets up (measured: no gain, profiles/tuning_r1.md)
 #endif
+#ifndef MSP_CULL_BOX_SMEM
+#define MSP_CULL_BOX_SMEM 1    // 1: the warp's 8 group boxes live in SMEM (2 LDS.128 per frame) instead of 6 registers, two of which spilled
+#endif
+#ifndef MSP_CULL_BOX_ADDR
+#define MSP_CULL_BOX_ADDR 1    // 1 (with BOX_SMEM): the lane's box address is kept in a register (opaque) instead of being re-derived every frame
+#endif
+#ifndef MSP_CULL_PIPELINE
+#define MSP_CULL_PIPELINE 0    // 1: the depth gathers of a pair of groups are consumed one loop iteration later (measured slower: profiles/tuning_r1.md)
+#endif
 #ifndef MSP_CULL_MAGIC_RINT
 #define MSP_CULL_MAGIC_RINT 1  // 1: rint(t) as (t + 1.5*2^23) - 1.5*2^23 on the FMA pipe instead of FRND on the XU pipe (exact for |t| < 2^22)
 #endif
@@ -129,6 +138,9 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   __shared__ __align__(16) double s_w[kCullFramesPerCta * 16];
 #endif
   __shared__ __align__(16) CullFrameConsts s_c[kCullFramesPerCta];
+#if MSP_CULL_BOX_SMEM
+  __shared__ __align__(16) float s_box[kCullWarps][kCullPtsPerLane][8];  // per group: centre xyz, -, half size xyz, - (re-centred)
+#endif
   __shared__ uint32_t s_words[kCullWarps][kCullPtsPerLane];
   __shared__ uint8_t s_q[kCullWarps][kCullWarpPoints];
   __shared__ uint8_t s_flist[kCullFramesPerCta];  // frames of this chunk in which the tile may be visible
@@ -280,6 +292,12 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
         // an empty group has inf - inf = NaN in its centre: every test on it is false, the group is skipped
       }
     }
+#if MSP_CULL_BOX_SMEM
+    if (lane < kCullPtsPerLane) {
+      *reinterpret_cast<float4*>(&s_box[warp][lane][0]) = make_float4(bcx, bcy, bcz, 0.f);
+      *reinterpret_cast<float4*>(&s_box[warp][lane][4]) = make_float4(bhx, bhy, bhz, 0.f);
+    }
+#endif
     const uint32_t ux = __reduce_max_sync(0xffffffffu, __float_as_uint(ex));
     const uint32_t uy = __reduce_max_sync(0xffffffffu, __float_as_uint(ey));
     const uint32_t uz = __reduce_max_sync(0xffffffffu, __float_as_uint(ez));
@@ -369,6 +387,10 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   // register instead of being re-derived from the thread id at every use (8 instructions per point at 64 registers)
   uint32_t s_lane = (uint32_t)__cvta_generic_to_shared(s_rel + 3 * (warp * kCullWarpPoints + lane));
   asm volatile("" : "+r"(s_lane));
+#if MSP_CULL_BOX_SMEM && MSP_CULL_BOX_ADDR
+  uint32_t s_box_lane = (uint32_t)__cvta_generic_to_shared(&s_box[warp][lane & 7][0]);
+  asm volatile("" : "+r"(s_box_lane));
+#endif
   unsigned int st_f32 = 0, st_exact = 0;
 
   // float32 evaluation of one group's point on this lane (branch-free; see the header comment for the bounds)
@@ -489,8 +511,21 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     uint32_t gm = 0u;
     {
       const float4 a = *reinterpret_cast<const float4*>(c.box[lane >> 3]);
+#if MSP_CULL_BOX_SMEM && MSP_CULL_BOX_ADDR
+      float4 bc, bh;
+      asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bc.x), "=f"(bc.y), "=f"(bc.z), "=f"(bc.w) : "r"(s_box_lane));
+      asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(bh.x), "=f"(bh.y), "=f"(bh.z), "=f"(bh.w) : "r"(s_box_lane));
+#elif MSP_CULL_BOX_SMEM
+      const float4 bc = *reinterpret_cast<const float4*>(&s_box[warp][lane & 7][0]);
+      const float4 bh = *reinterpret_cast<const float4*>(&s_box[warp][lane & 7][4]);
+#endif
+#if MSP_CULL_BOX_SMEM
+      const float v = fmaf(a.x, bc.x, fmaf(a.y, bc.y, fmaf(a.z, bc.z, a.w)));
+      const float r = __fmaf_ru(fabsf(a.x), bh.x, __fmaf_ru(fabsf(a.y), bh.y, __fmul_ru(fabsf(a.z), bh.z)));
+#else
       const float v = fmaf(a.x, bcx, fmaf(a.y, bcy, fmaf(a.z, bcz, a.w)));
       const float r = __fmaf_ru(fabsf(a.x), bhx, __fmaf_ru(fabsf(a.y), bhy, __fmul_ru(fabsf(a.z), bhz)));
+#endif
       const uint32_t gb = __ballot_sync(0xffffffffu, __fadd_ru(v, r) >= -B);
       gm = gb & (gb >> 8) & (gb >> 16) & (gb >> 24) & 0xffu;
     }
@@ -507,6 +542,48 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
         zrow = reinterpret_cast<unsigned int*>(p.zbuf + f * p.depth_stride);
       }
       if (p.stats != nullptr) st_f32 += __popc(gm);
+#if MSP_CULL_PIPELINE
+      // ---- B + C, software-pipelined inside the frame: iteration k projects pair k and issues its two depth gathers, then
+      // finishes pair k-1 (depth comparison, ballots, queueing), whose gathers have had a whole projection to land.
+      // A single left-over group travels as a pair whose second slot is empty (j = -1: no lane owns its word).
+      Lane32 q0, q1;
+      int qj0 = -1, qj1 = -1;
+      bool have = false;
+      q0.zf = q1.zf = 0.f, q0.raw = q1.raw = 0u, q0.go = q1.go = q0.unc = q1.unc = false;
+      for (;;) {
+        const bool more = gm != 0u;  // warp-uniform
+        Lane32 r0, r1;
+        int j0 = -1, j1 = -1;
+        r0.zf = r1.zf = 0.f, r0.raw = r1.raw = 0u, r0.go = r1.go = r0.unc = r1.unc = false;
+        if (more) {
+          j0 = __ffs(gm) - 1;
+          gm &= gm - 1u;
+          r0 = eval32(j0, a0, a2, az, B, B2, ct1, half_ct0, dm);
+          if (gm != 0u) {
+            j1 = __ffs(gm) - 1;
+            gm &= gm - 1u;
+            r1 = eval32(j1, a0, a2, az, B, B2, ct1, half_ct0, dm);
+          }
+        }
+        if (have) {
+          bool v0, u0, v1, u1;
+          cmp32(q0, Bz, v0, u0);
+          cmp32(q1, Bz, v1, u1);
+          const uint32_t bv0 = __ballot_sync(0xffffffffu, v0), bv1 = __ballot_sync(0xffffffffu, v1);
+          if (lane == qj0) myword = bv0;
+          if (lane == qj1) myword = bv1;
+          const uint32_t bu0 = __ballot_sync(0xffffffffu, q0.unc | u0), bu1 = __ballot_sync(0xffffffffu, q1.unc | u1);
+          if ((bu0 | bu1) != 0u) {  // rare, warp-uniform
+            if (q0.unc | u0) s_q[warp][nq + __popc(bu0 & lt)] = (uint8_t)((qj0 << 5) | lane);
+            nq += __popc(bu0);
+            if (q1.unc | u1) s_q[warp][nq + __popc(bu1 & lt)] = (uint8_t)((qj1 << 5) | lane);
+            nq += __popc(bu1);
+          }
+        }
+        if (!more) break;
+        q0 = r0, q1 = r1, qj0 = j0, qj1 = j1, have = true;
+      }
+#else
       // ---- B + C: candidate groups two at a time (two independent dependency chains per lane), then a leftover
       while (gm & (gm - 1u)) {
         const int j0 = __ffs(gm) - 1;
@@ -542,6 +619,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
           nq += __popc(bu0);
         }
       }
+#endif
       if (p.stats != nullptr) st_exact += (lane == 0) ? nq : 0;
     }
 
