@@ -293,3 +293,47 @@ def test_l2_tables_cli_single_rank(disk, relations, tmp_path):
     with open(tmp_path / "ov.pkl", "rb") as f:
         ov = pickle.load(f)
     assert list(ov) == [s.scene_id for s in scenes] and all("object_to_images" in x for x in ov.values())
+
+
+def test_coverage_shard_drivers_layout_cpu(gen, disk, tmp_path, monkeypatch):
+    """object_perception.coverage_main / process_split_objects: the shard directories and file names of
+    single_object_coverage_finder.py (SOCF:380-420, 296-340) feed merge_split and the writer unchanged.  The per-scene search is
+    stubbed here (it needs the GPU; tests/test_handler_tables.py covers it) — this checks the host-side plumbing."""
+    from multi_spatialmllm_b200 import object_perception as op, tables
+    scenes, _, root, info = disk
+    h = _handler(root, info)
+    full = gen.object_coverage_info(scenes)
+    ov = {s.scene_id: {"object_to_images": {o: [] for o in full[s.scene_id]}} for s in scenes}
+    ov_file = tmp_path / "object_visibility.pkl"
+    with open(ov_file, "wb") as f:
+        pickle.dump(ov, f)
+    seen = []
+    monkeypatch.setattr(tables, "device_scene_from_handler", lambda hh, sid, dev="cuda:0": (None, []))
+
+    def fake_scene(scene_infos, scene_id, sc, image_ids, object_visibility, max_images=5):
+        seen.append(scene_id)
+        assert object_visibility == ov[scene_id]
+        return {o: {"height": d, "length": {1: d.get(1, [])}, "width": {}} for o, d in full[scene_id].items()}
+
+    monkeypatch.setattr(tables, "object_coverage_scene", fake_scene)
+    splits = {"val": {"scene_info_path": h, "visibility_parquet_file": None, "object_visibility_file": str(ov_file),
+                      "output_dir": str(tmp_path / "evaluation_data" / "object_perception")}}
+    ids = h.get_all_scene_ids()
+    op.coverage_main(["--split", "val", "--start", "1", "--end", "2"], splits=splits)
+    op.coverage_main(["--split", "val", "--start", "0", "--end", "1"], splits=splits)
+    assert seen == [ids[1], ids[0]]
+    base = tmp_path / "evaluation_data" / "object_perception"
+    assert sorted(os.listdir(base)) == ["val_0_1", "val_1_2"]
+    assert sorted(os.listdir(base / "val_0_1")) == [f"val_object_coverage_{d}_0_1.pkl" for d in ("height", "length", "width")]
+    merged = op.merge_split("val", str(base), str(base))
+    assert merged["height"] == {sid: full[sid] for sid in ids} and list(merged["height"]) == ids
+    assert merged["width"] == {sid: {o: {} for o in full[sid]} for sid in ids}
+    with pytest.raises(ValueError):
+        op.coverage_main(["--split", "test", "--start", "0"], splits=splits)
+    res = op.process_split_objects("val", h, None, str(ov_file), str(tmp_path / "whole"))
+    assert sorted(os.listdir(tmp_path / "whole")) == ["coverage_finding_warning_objects.txt"] + \
+        [f"val_object_coverage_{d}.pkl" for d in ("height", "length", "width")]
+    assert res["height"] == merged["height"]
+    random.seed(1)
+    out = op.build_lwh_qa_samples(h, str(base / "merged_val_object_coverage_height.pkl"), "height", "val", str(tmp_path / "qa"))
+    assert sum(len(v) for v in out.values()) > 0 and all(f.startswith("object_perception_height_k") for f in os.listdir(tmp_path / "qa"))
