@@ -348,3 +348,22 @@ def track_pair_sample_values(world, cam, w2c, fxfycxcy, f1, f2, p, image_h, imag
         "xyz_mm": tuple(round(float(c) * 1000) for c in dcam),
         "dcam": dcam, "point_moving": int(moving), "cam_moving": int(cam_moving),
     }
+
+
+def rigid_body_groups(points: np.ndarray, threshold: float = 0.1, smoothing_factor: float = 0.01, min_size: int = 5):
+    """OM:34-105: accumulate |d_t - d_{t-1}| of all pair distances where it exceeds ``smoothing_factor``, average-linkage
+    clustering of the accumulated matrix cut at ``threshold``, groups with more than ``min_size`` members.
+    Returns (groups, condensed accumulated loss)."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from scipy.spatial.distance import pdist
+    points = np.asarray(points, dtype=np.float64)
+    loss = np.zeros(points.shape[1] * (points.shape[1] - 1) // 2)
+    prev = pdist(points[0])
+    for t in range(1, points.shape[0]):
+        cur = pdist(points[t])
+        change = np.abs(cur - prev)
+        loss += np.where(change > smoothing_factor, change, 0)
+        prev = cur
+    labels = fcluster(linkage(loss, method="average"), threshold, criterion="distance")
+    groups = [np.where(labels == i)[0].tolist() for i in range(1, int(labels.max()) + 1)]
+    return [g for g in groups if len(g) > min_size], loss

@@ -248,3 +248,79 @@ def test_speculative_replay_equals_row_by_row_cpu(name, pair_setup):
         outs.append((json.loads(json.dumps(samples)), rnd.random(), eng.replans))
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
     assert outs[0][2] > 3 and any(s is None for s in outs[0][0]) and any(s is not None for s in outs[0][0])
+
+
+# ------------------------------------------------------------------------------------------------
+# TAPVid-3D worker: DeviceVideo and the all-pair distance launch replaced by the oracle
+# ------------------------------------------------------------------------------------------------
+class OracleVideo:
+    def __init__(self, tracks_xyz, w2c, fxfycxcy, image_hw, device=None):
+        self.tracks = np.asarray(tracks_xyz, np.float32)
+        self.T, self.N = self.tracks.shape[:2]
+        self.w2c_h = np.asarray(w2c, np.float64).reshape(self.T, 4, 4)
+        self.w2c = torch.from_numpy(self.w2c_h.reshape(self.T, 16).copy())
+        self.intr, self.image_hw, self.device = np.asarray(fxfycxcy, np.float64), tuple(int(v) for v in image_hw), "cpu"
+        self.world = self.uvn = self.permille = self.valid = None
+
+    def project(self):
+        cam = self.tracks.astype(np.float64)
+        H, W = self.image_hw
+        world = og.tracks_to_world(cam, self.w2c_h)
+        uvn, pm = np.zeros((self.T, self.N, 2)), np.zeros((self.T, self.N, 2), np.int32)
+        valid = np.zeros((self.T, self.N), np.uint8)
+        for t in range(self.T):
+            for n in range(self.N):
+                r = og.track_project_point(cam[t, n], self.intr, H, W)
+                if r is not None:
+                    uvn[t, n], valid[t, n] = r, 1
+                    pm[t, n] = (round(r[0] * 1000), round(r[1] * 1000))
+        self.world_h = world
+        self.world, self.uvn, self.permille, self.valid = (torch.from_numpy(np.ascontiguousarray(a)) for a in (world, uvn, pm, valid))
+        return self
+
+    def pair_displacement(self, triples):
+        out = np.zeros((len(triples), 5))
+        for k, (f1, f2, p) in enumerate(np.asarray(triples).reshape(-1, 3).tolist()):
+            d = self.world_h[f2, p] - self.world_h[f1, p]
+            c1, c2 = np.linalg.inv(self.w2c_h[f1]), np.linalg.inv(self.w2c_h[f2])
+            out[k, 0] = np.linalg.norm(d)
+            out[k, 1:4] = (self.w2c_h[f1] @ np.concatenate([d, [0.0]]))[:3]
+            out[k, 4] = np.linalg.norm(c2[:3, 3] - c1[:3, 3])
+        return torch.from_numpy(out)
+
+    def rigid_body_groups(self, threshold=0.1, smoothing_factor=0.01, min_size=5):
+        return og.rigid_body_groups(self.tracks, threshold, smoothing_factor, min_size)
+
+
+def _oracle_all_pair_distances(vid, track_ids, visible_frames):
+    if vid.world is None:
+        vid.project()
+    return [og.track_pair_distances(vid.world_h[:, p], np.asarray(vf)) for p, vf in zip(track_ids, visible_frames)]
+
+
+@pytest.mark.parametrize("case_index", [0, 1])
+def test_tapvid_worker_host_logic_matches_reference_cpu(case_index, monkeypatch):
+    """sample_video_pairs (static / moving split, 10-bin sampling, augmentation: the reference's RNG stream) and the sample
+    formatter over oracle answers reproduce the reference's generate_qa_training_single_scene."""
+    from multi_spatialmllm_b200 import streams, tapvid
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "tapvid_sampling.json.gz"), "rt") as f:
+        g = json.load(f)
+    case = g["cases"][case_index]
+    vs, T, N, G, qt, npg, ratio, rs = case["case"]
+    v = synth.make_video(vs, n_frames=T, n_tracks=N, n_groups=G, image_hw=(36, 64))
+    v.tracks_xyz[:, : N // 6] = v.tracks_xyz[:1, : N // 6]
+    monkeypatch.setattr(tapvid, "DeviceVideo", OracleVideo)
+    monkeypatch.setattr(tapvid, "all_pair_distances", _oracle_all_pair_distances)
+    video = {"images_jpeg_bytes": None, "fx_fy_cx_cy": v.fxfycxcy, "tracks_XYZ": v.tracks_xyz, "visibility": v.visibility,
+             "extrinsics_w2c": v.w2c}
+    random.seed(rs)
+    out = tapvid.generate_video_samples(video, v.video_id, qt, npoints_per_group=npg, npairs_per_bin=1e8, image_hw=(36, 64),
+                                        augment=True, augment_ratio=ratio,
+                                        templates=streams.Templates({f"object_movement:{qt}": g["templates"]}), rnd=random)
+    after = random.random()
+    got = json.loads(json.dumps(out))
+    assert [e["id"] for e in got] == [w["id"] for w in case["samples"]]
+    for e, w in zip(got, case["samples"]):
+        for key in ("gt_value", "image", "conversations", "p1", "p2", "point_moving", "cam_moving"):
+            assert e[key] == w[key], (e["id"], key)
+    assert after == case["random_after"]

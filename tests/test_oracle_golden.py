@@ -210,3 +210,16 @@ def test_drawing_oracle_matches_cv2_live():
         cv2.putText(a, ch, (20, 45), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (1, 2, 3), 2)
         drawing.stamp_glyph(b, *atlas.mask(ch), (20, 45), (1, 2, 3))
         np.testing.assert_array_equal(a, b)
+
+
+def test_oracle_rigid_body_groups_match_reference(golden_tapvid):
+    """oracle.rigid_body_groups == the reference's rigid_body_segmentation + filter_large_groups (engines_small.json)."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "engines_small.json")) as f:
+        eg = json.load(f)
+    groups, loss = og.rigid_body_groups(golden_tapvid["tracks_xyz"], min_size=5)
+    assert groups == eg["rigid_body_groups_filtered"]
+    groups_all, _ = og.rigid_body_groups(golden_tapvid["tracks_xyz"], min_size=0)
+    assert groups_all == [g for g in eg["rigid_body_groups"] if len(g) > 0]
+    n = golden_tapvid["tracks_xyz"].shape[1]
+    assert loss.shape == (n * (n - 1) // 2,) and (loss >= 0).all()
