@@ -50,6 +50,22 @@ constexpr int kCullMaxObjects = 63;
 #ifndef MSP_CULL_BOX_SMEM
 #define MSP_CULL_BOX_SMEM 1    // 1: the warp's 8 group boxes live in SMEM (2 LDS.128 per frame) instead of 6 registers, two of which spilled
 #endif
+#ifndef MSP_CULL_DEFER_EXACT
+#define MSP_CULL_DEFER_EXACT 0     // 1 (visibility mode): lanes queued for the exact float64 path are collected per warp ACROSS frames and
+                                   // evaluated 32 at a time, OR-ing the few visible bits into the already stored mask words, instead of
+                                   // running the ~200-instruction exact path for one or two lanes in ~15 % of the warp-frames
+                                   // (NOT YET MEASURED: drafted at the end of round 1, profiles/tuning_r1.md)
+#endif
+#ifndef MSP_CULL_STRIDED_GROUPS
+#define MSP_CULL_STRIDED_GROUPS 0  // 1: warp w owns the tile's groups w, w+8, w+16, ... instead of 8 consecutive ones, so that the eight
+                                   // warps of a CTA sample the tile's extent alike and finish their frames together (NOT YET MEASURED:
+                                   // drafted at the end of round 1 against the end-of-CTA barrier share, profiles/tuning_r1.md)
+#endif
+#if MSP_CULL_STRIDED_GROUPS
+#define MSP_CULL_GROUP(warp, j) ((j) * kCullWarps + (warp))
+#else
+#define MSP_CULL_GROUP(warp, j) ((warp) * kCullPtsPerLane + (j))
+#endif
 #ifndef MSP_CULL_BOX_ADDR
 #define MSP_CULL_BOX_ADDR 1    // 1 (with BOX_SMEM): the lane's box address is kept in a register (opaque) instead of being re-derived every frame
 #endif
@@ -143,6 +159,10 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
 #endif
   __shared__ uint32_t s_words[kCullWarps][kCullPtsPerLane];
   __shared__ uint8_t s_q[kCullWarps][kCullWarpPoints];
+#if MSP_CULL_DEFER_EXACT
+  constexpr uint32_t kDeferCap = 64;                        // fill < 32 between frames, at most 32 appended per frame
+  __shared__ uint16_t s_dq[kCullWarps][kDeferCap];          // (frame in chunk << 8) | (group << 5) | lane
+#endif
   __shared__ uint8_t s_flist[kCullFramesPerCta];  // frames of this chunk in which the tile may be visible
   __shared__ int s_nlist;
   __shared__ int s_red[9];  // ordered-int min xyz, max xyz, then uint max |x'|,|y'|,|z'|
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   if (COUNT) {
 #pragma unroll
     for (int j = 0; j < kCullPtsPerLane; ++j) {
-      const int idx = warp * kCullWarpPoints + j * 32 + lane;
+      const int idx = MSP_CULL_GROUP(warp, j) * 32 + lane;
       uint32_t id = (idx < cnt) ? (uint32_t)__ldg(p.inst + base + idx) : 0u;
       if (id > (uint32_t)p.n_objects) id = 0u;
       const uint32_t first = __shfl_sync(0xffffffffu, id, 0);
@@ -228,7 +248,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     float lx = finf, ly = finf, lz = finf, hx = -finf, hy = -finf, hz = -finf;
 #pragma unroll
     for (int j = 0; j < kCullPtsPerLane; ++j) {
-      const int idx = warp * kCullWarpPoints + j * 32 + lane;
+      const int idx = MSP_CULL_GROUP(warp, j) * 32 + lane;
       px[j] = py[j] = pz[j] = qnan;  // slots beyond the tile and non-finite points: every comparison on them is false
       if (idx < cnt) {
         float x, y, z;
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
         // float64 inputs: subtract the centre in float64 and round ONCE, so that the error of x' is u |x'| and not
         // u |x| (rounding the coordinate itself to float32 first loses |x| * 2^-24: metres at kilometre offsets)
         if (px[j] == px[j]) {
-          const int idx = warp * kCullWarpPoints + j * 32 + lane;
+          const int idx = MSP_CULL_GROUP(warp, j) * 32 + lane;
           double x64, y64, z64;
           PtTraits<DT>::load(s_pts, idx, x64, y64, z64);
           px[j] = __double2float_rn(x64 - (double)tcx);
@@ -306,7 +326,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   __syncthreads();  // every thread has read its original coordinates: the buffer may now be overwritten
 #pragma unroll
   for (int j = 0; j < kCullPtsPerLane; ++j) {
-    const int idx = warp * kCullWarpPoints + j * 32 + lane;
+    const int idx = MSP_CULL_GROUP(warp, j) * 32 + lane;
     s_rel[3 * idx + 0] = px[j], s_rel[3 * idx + 1] = py[j], s_rel[3 * idx + 2] = pz[j];
   }
 
@@ -379,13 +399,19 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   }
   __syncthreads();
 
+#if MSP_CULL_STRIDED_GROUPS
+  // lane j (< 8) owns the mask word of the warp's group j: word0 + lane is that word's index
+  const int64_t word0 = (int64_t)blockIdx.x * (kCullTilePoints / 32) + MSP_CULL_GROUP(warp, lane & (kCullPtsPerLane - 1)) - lane;
+#else
   const int64_t word0 = (int64_t)blockIdx.x * (kCullTilePoints / 32) + warp * kCullPtsPerLane;
+#endif
   const uint32_t lt = (1u << lane) - 1u;
   const bool word_ok = (lane < kCullPtsPerLane) && (word0 + lane < p.mask_stride);
   uint32_t* mask_ptr = p.mask + (int64_t)f0 * p.mask_stride + word0 + lane;
   // this lane's point of group j is at shared address s_lane + 384 j; the address is made opaque so that it is kept in a
   // register instead of being re-derived from the thread id at every use (8 instructions per point at 64 registers)
-  uint32_t s_lane = (uint32_t)__cvta_generic_to_shared(s_rel + 3 * (warp * kCullWarpPoints + lane));
+  constexpr uint32_t kGroupStrideBytes = (uint32_t)(MSP_CULL_GROUP(0, 1) - MSP_CULL_GROUP(0, 0)) * 32u * 12u;  // 384 / 3072
+  uint32_t s_lane = (uint32_t)__cvta_generic_to_shared(s_rel + 3 * (MSP_CULL_GROUP(warp, 0) * 32 + lane));
   asm volatile("" : "+r"(s_lane));
 #if MSP_CULL_BOX_SMEM && MSP_CULL_BOX_ADDR
   uint32_t s_box_lane = (uint32_t)__cvta_generic_to_shared(&s_box[warp][lane & 7][0]);
@@ -405,7 +431,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
                     float half_ct0, unsigned long long dmb) -> Lane32 {
     float x, y, z;
     {
-      const uint32_t q = s_lane + 384u * (uint32_t)j;
+      const uint32_t q = s_lane + kGroupStrideBytes * (uint32_t)j;
       asm("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(q));
       asm("ld.shared.f32 %0, [%1+4];" : "=f"(y) : "r"(q));
       asm("ld.shared.f32 %0, [%1+8];" : "=f"(z) : "r"(q));
@@ -440,7 +466,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       // group's minimum touch memory - one atomic per (warp, pixel) instead of one per point
       const uint32_t act = __ballot_sync(0xffffffffu, r.go);
       if (r.go) {
-        const int idx = warp * kCullWarpPoints + j * 32 + lane;
+        const int idx = MSP_CULL_GROUP(warp, j) * 32 + lane;
         double x64, y64, z64;
         PtTraits<DT>::load(p.pts, base + idx, x64, y64, z64);
         const uint32_t zb = __float_as_uint(__double2float_rn(row_dot_h(wz, x64, y64, z64)));
@@ -451,7 +477,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       }
 #else
       if (r.go) {
-        const int idx = warp * kCullWarpPoints + j * 32 + lane;
+        const int idx = MSP_CULL_GROUP(warp, j) * 32 + lane;
         double x64, y64, z64;
         PtTraits<DT>::load(p.pts, base + idx, x64, y64, z64);
         const double zref = row_dot_h(wz, x64, y64, z64);
@@ -499,6 +525,31 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
   __syncthreads();
   const int nlist = s_nlist;
 
+#if MSP_CULL_DEFER_EXACT
+  uint32_t dq = 0;  // warp-uniform fill of s_dq[warp]
+  // one deferred point on this lane: exact re-evaluation; a visible point is OR-ed into its (already stored) mask word and
+  // added to the count histogram.  Callers order the plain mask stores before this with __syncwarp().
+  auto exact_deferred = [&](uint32_t e) {
+    const int fi2 = (int)(e >> 8), j = (int)((e >> 5) & 7u), sl = (int)(e & 31u);
+    const int idx = MSP_CULL_GROUP(warp, j) * 32 + sl;
+    const int64_t f2 = f0 + fi2;
+    const double* w = s_w + fi2 * 16;
+    const bool fstd = s_c[fi2].std_frame != 0;
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (idx < cnt) PtTraits<DT>::load(p.pts, base + idx, x, y, z);
+    const Proj pr = fstd ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
+    if (idx < cnt && in_image(pr, p.g) && pr.z > 0.0) {
+      const int di = depth_index(pr, p.g);
+      if (depth_test(pr.z, ldg_u16_nc(p.depth + f2 * p.depth_stride + di), p.g)) {
+        atomicOr(p.mask + f2 * p.mask_stride + (int64_t)blockIdx.x * (kCullTilePoints / 32) + MSP_CULL_GROUP(warp, j), 1u << sl);
+        if (COUNT) {
+          const uint32_t id = (uint32_t)__ldg(p.inst + base + idx);
+          if (id != 0u && id <= (uint32_t)p.n_objects) atomicAdd(&s_cnt[fi2 * kCntWords + (id >> 1)], 1u << ((id & 1u) * 16u));
+        }
+      }
+    }
+  };
+#endif
   for (int li = 0; li < nlist; ++li) {
     const int fi = s_flist[li];
     const CullFrameConsts& c = s_c[fi];
@@ -624,7 +675,12 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
     }
 
     // ---- D: exact float64 reference-order evaluation of the queued lanes (rare)
+#if MSP_CULL_DEFER_EXACT
+    const bool defer = (MODE == 0) && nq != 0u && nq <= 32u;  // warp-uniform; larger bursts (non-standard frames) stay immediate
+    if (nq != 0u && !defer) {
+#else
     if (nq != 0u) {
+#endif
       __syncwarp();
       const double* w = s_w + fi * 16;
       const bool fstd = c.std_frame != 0;
@@ -633,7 +689,7 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
         if (t < nq) {
           const uint32_t code = s_q[warp][t];
           const int j = code >> 5, sl = code & 31;
-          const int idx = warp * kCullWarpPoints + j * 32 + sl;
+          const int idx = MSP_CULL_GROUP(warp, j) * 32 + sl;
           double x = 0.0, y = 0.0, z = 0.0;
           if (idx < cnt) PtTraits<DT>::load(p.pts, base + idx, x, y, z);
           const Proj pr = fstd ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
@@ -678,7 +734,26 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
         }
       }
     }
+#if MSP_CULL_DEFER_EXACT
+    if (defer) {  // after this frame's mask words have been stored
+      __syncwarp();
+      if (lane < nq) s_dq[warp][dq + lane] = (uint16_t)(((uint32_t)fi << 8) | s_q[warp][lane]);
+      dq += nq;
+      if (dq >= 32u) {
+        __syncwarp();  // queue entries and the plain mask stores of lanes 0..7 are visible to the whole warp
+        exact_deferred(s_dq[warp][dq - 32u + lane]);
+        dq -= 32u;
+        __syncwarp();
+      }
+    }
+#endif
   }
+#if MSP_CULL_DEFER_EXACT
+  if (dq != 0u) {
+    __syncwarp();
+    if (lane < dq) exact_deferred(s_dq[warp][lane]);
+  }
+#endif
   if (COUNT) {
     __syncthreads();
     const int o = tid & 63;  // 64 ids per frame row, 4 frame rows per pass
