@@ -54,12 +54,13 @@ constexpr int kCullMaxObjects = 63;
 #define MSP_CULL_DEFER_EXACT 0     // 1 (visibility mode): lanes queued for the exact float64 path are collected per warp ACROSS frames and
                                    // evaluated 32 at a time, OR-ing the few visible bits into the already stored mask words, instead of
                                    // running the ~200-instruction exact path for one or two lanes in ~15 % of the warp-frames
-                                   // (NOT YET MEASURED: drafted at the end of round 1, profiles/tuning_r1.md)
+                                   // (end of round 1: -10 % on a 200 k x 512 scene with bit-identical masks and counts,
+                                   // profiles/variant_check_r1.txt; not yet through the whole GPU suite, hence still off)
 #endif
 #ifndef MSP_CULL_STRIDED_GROUPS
 #define MSP_CULL_STRIDED_GROUPS 0  // 1: warp w owns the tile's groups w, w+8, w+16, ... instead of 8 consecutive ones, so that the eight
-                                   // warps of a CTA sample the tile's extent alike and finish their frames together (NOT YET MEASURED:
-                                   // drafted at the end of round 1 against the end-of-CTA barrier share, profiles/tuning_r1.md)
+                                   // warps of a CTA sample the tile's extent alike and finish their frames together (end of round 1:
+                                   // -2.6 %, bit-identical output, profiles/variant_check_r1.txt; not yet through the whole GPU suite)
 #endif
 #if MSP_CULL_STRIDED_GROUPS
 #define MSP_CULL_GROUP(warp, j) ((j) * kCullWarps + (warp))
@@ -739,8 +740,8 @@ __global__ void __launch_bounds__(kCullThreads, MSP_CULL_MINBLOCKS) k_frame_cull
       __syncwarp();
       if (lane < nq) s_dq[warp][dq + lane] = (uint16_t)(((uint32_t)fi << 8) | s_q[warp][lane]);
       dq += nq;
+      __syncwarp();  // s_q may be refilled by the next frame; queue entries and the plain mask stores of lanes 0..7 are visible
       if (dq >= 32u) {
-        __syncwarp();  // queue entries and the plain mask stores of lanes 0..7 are visible to the whole warp
         exact_deferred(s_dq[warp][dq - 32u + lane]);
         dq -= 32u;
         __syncwarp();
