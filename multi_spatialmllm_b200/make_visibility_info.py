@@ -15,7 +15,6 @@ from __future__ import annotations
 import os
 import pickle
 
-import numpy as np
 
 from . import engine, tables
 from .handler.info_handler import SceneInfoHandler

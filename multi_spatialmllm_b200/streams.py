@@ -23,7 +23,6 @@ from __future__ import annotations
 import importlib.util
 import json
 import os
-import sys
 
 import numpy as np
 
