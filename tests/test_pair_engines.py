@@ -337,3 +337,39 @@ def test_coverage_shard_drivers_layout_cpu(gen, disk, tmp_path, monkeypatch):
     random.seed(1)
     out = op.build_lwh_qa_samples(h, str(base / "merged_val_object_coverage_height.pkl"), "height", "val", str(tmp_path / "qa"))
     assert sum(len(v) for v in out.values()) > 0 and all(f.startswith("object_perception_height_k") for f in os.listdir(tmp_path / "qa"))
+
+
+def test_reference_templates_are_read_without_importing_cpu(tmp_path):
+    """load_reference_templates parses the phrasings out of a checkout through the AST: module-level side effects of the
+    reference files (RNG seeding, heavy imports, a failing import) never run.  A miniature checkout stands in here; when the
+    real one is mounted (build container) it is read too."""
+    from multi_spatialmllm_b200 import object_perception as op, pair_engines
+    root = tmp_path / "ref"
+    (root / "spatial_engine/camera_movement").mkdir(parents=True)
+    (root / "spatial_engine/visual_correspondence").mkdir(parents=True)
+    (root / "spatial_engine/object_perception").mkdir(parents=True)
+    (root / "spatial_engine/camera_movement/TEMPLATES.py").write_text(
+        'QUESTION_TEMPLATES = {"x_movement": ["q {x_movement}"]}\nTASK_DESCRIPTION = ["t0", "t1"]\nANSWER_TEMPLATES = {"x_movement": ["a"]}\n')
+    for name in ("visual_correspondence_qa_engine_coor_2_coor.py", "visual_correspondence_qa_engine_dot_2_multichoice.py"):
+        (root / "spatial_engine/visual_correspondence" / name).write_text(
+            'import this_module_does_not_exist\nraise RuntimeError("must not run")\nTASK_DESCRIPTION = ["vt"]\n'
+            'TEMPLATES = {"questions": ["vq {x1}"], "answers": ["va {x2}"]}\n')
+    (root / "spatial_engine/object_perception/single_object_perception_engine.py").write_text(
+        'import random\nrandom.seed(1)\nASK_DESCRIPTION = ["ot"]\nQUESTION_TEMPLATES = ["oq {dimension}"]\nANSWER_TEMPLATES = ["oa {value_mm}"]\n')
+    t = pair_engines.load_reference_templates(str(root), "camera_movement")
+    assert t == {"task": ["t0", "t1"], "questions": {"x_movement": ["q {x_movement}"]}, "answers": {"x_movement": ["a"]}}
+    for eng in ("visual_correspondence", "visual_correspondence_dot"):
+        assert pair_engines.load_reference_templates(str(root), eng) == {"task": ["vt"], "questions": ["vq {x1}"], "answers": ["va {x2}"]}
+    assert op.load_reference_templates(str(root)) == {"task": ["ot"], "questions": ["oq {dimension}"], "answers": ["oa {value_mm}"]}
+    real = os.environ.get("MSP_REFERENCE_ROOT", "/root/reference")
+    if os.path.isdir(os.path.join(real, "spatial_engine")):
+        state = random.getstate()
+        cm = pair_engines.load_reference_templates(real, "camera_movement")
+        assert set(cm["questions"]) == set(pair_engines.CAMERA_QUESTION_TYPES) and len(cm["task"]) >= 5
+        vc = pair_engines.load_reference_templates(real, "visual_correspondence")
+        assert all("{x1}" in q for q in vc["questions"]) and len(vc["answers"]) >= 5
+        vd = pair_engines.load_reference_templates(real, "visual_correspondence_dot")
+        assert all("{correct_label}" in a for a in vd["answers"])
+        so = op.load_reference_templates(real)
+        assert len(so["task"]) >= 5 and all("{value_mm}" in a for a in so["answers"])
+        assert random.getstate() == state                      # nothing was executed: the global RNG is untouched
