@@ -373,3 +373,41 @@ def test_reference_templates_are_read_without_importing_cpu(tmp_path):
         so = op.load_reference_templates(real)
         assert len(so["task"]) >= 5 and all("{value_mm}" in a for a in so["answers"])
         assert random.getstate() == state                      # nothing was executed: the global RNG is untouched
+
+
+def test_sample_dataframe_differential_against_live_reference_cpu():
+    """When the reference checkout is mounted (build container): 60 random overlap tables through the reference's own
+    sample_dataframe and through this repo's, same rows in the same order and the same NumPy RNG position every time."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference checkout not mounted")
+    import contextlib
+    import io
+    import sys
+    from multi_spatialmllm_b200 import pair_engines
+    ref_shim.import_reference()
+    sys.path.insert(0, os.path.join(ref_shim.REFERENCE_ROOT, "spatial_engine", "camera_movement"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        from spatial_engine.camera_movement import camera_movement_engine_train_val as cme
+    rng = np.random.default_rng(7)
+    for case in range(60):
+        rows = int(rng.integers(0, 300))
+        ov = rng.uniform(-5, 110, rows)
+        ov[rng.random(rows) < 0.15] = 0.0
+        ov[rng.random(rows) < 0.05] = np.nan
+        snap = rng.random(rows) < 0.2
+        ov[snap] = np.round(ov[snap])
+        lo = int(rng.integers(0, 40))
+        step = int(rng.choice([1, 2, 5, 10]))
+        hi = lo + step * int(rng.integers(1, 30))
+        n_all, n_zero = int(rng.integers(0, 2 * rows + 2)), int(rng.integers(0, 20))
+        df = pd.DataFrame({"overlap": ov, "row": np.arange(rows)})
+        np.random.seed(case)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = cme.sample_dataframe(df, n_all, n_zero, lo, hi, step)
+        want_after = float(np.random.random())
+        np.random.seed(case)
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = pair_engines.sample_dataframe(df, n_all, n_zero, lo, hi, step)
+        assert [int(v) for v in got["row"]] == [int(v) for v in want["row"]], (case, rows, lo, hi, step, n_all, n_zero)
+        assert float(np.random.random()) == want_after, case
