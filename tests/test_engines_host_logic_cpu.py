@@ -93,6 +93,7 @@ def pair_setup(tmp_path_factory):
     info = ref_layout.write_split(scenes, root, name="scenes_train_val_info_i_D5.pkl")
     h = SceneInfoHandler(info, posed_images_root=os.path.join(root, "posed_images"),
                          instance_data_root=os.path.join(root, "scannet_instance_data"))
+    h._test_info, h._test_root = info, root                       # for the live-reference differential test
     cache = OracleCache(scenes)
     rows = []
     for s in scenes:                                               # the relations table, CFR:139-197 order
@@ -324,3 +325,66 @@ def test_tapvid_worker_host_logic_matches_reference_cpu(case_index, monkeypatch)
         for key in ("gt_value", "image", "conversations", "p1", "p2", "point_moving", "cam_moving"):
             assert e[key] == w[key], (e["id"], key)
     assert after == case["random_after"]
+
+
+@pytest.mark.parametrize("engine,seed,count,kw", [("visual_correspondence", 101, 50, {"max_points_per_pair": 2}),
+                                                   ("camera_movement", 103, 70, {"qtype": "pitch_movement"})])
+def test_pair_engines_differential_against_live_reference_cpu(engine, seed, count, kw, pair_setup, tmp_path):
+    """Seeds the goldens do not hold: the unmodified reference engine (when its checkout is mounted) and this repo's engine
+    over oracle answers, same tables, same seed -> the same JSONL and the same RNG positions."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference checkout not mounted")
+    import contextlib
+    import io
+    import pickle
+    import sys
+    from multi_spatialmllm_b200 import pair_engines
+    h, cache, parquet, golden = pair_setup
+    ref = ref_shim.import_reference()
+    sys.path.insert(0, os.path.join(ref_shim.REFERENCE_ROOT, "spatial_engine", "camera_movement"))
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    with quiet:
+        if engine == "camera_movement":
+            from spatial_engine.camera_movement import camera_movement_engine_train_val as mod
+        else:
+            from spatial_engine.visual_correspondence import visual_correspondence_qa_engine_coor_2_coor as mod
+    t = golden["templates"][engine]
+    if engine == "camera_movement":
+        mod.TASK_DESCRIPTION, mod.QUESTION_TEMPLATES, mod.ANSWER_TEMPLATES = t["task"], t["questions"], t["answers"]
+    else:
+        mod.TASK_DESCRIPTION, mod.TEMPLATES = t["task"], {k: v for k, v in t.items() if k != "task"}
+    # the reference handler on the same disk scenes (its own geometry), the oracle's visibility lists as its table
+    with quiet:
+        rh = ref.info_handler.SceneInfoHandler(h._test_info, posed_images_root=os.path.join(h._test_root, "posed_images"),
+                                               instance_data_root=os.path.join(h._test_root, "scannet_instance_data"))
+    rh.get_image_size = rh.get_image_shape
+    vis = {sid: {"image_to_points": {i: np.flatnonzero(sc.masks[f]).tolist() for i, f in row_of.items() if sc.valid[f]}}
+           for sid, (sc, row_of) in cache.scenes.items()}
+    vis_pkl = str(tmp_path / "vis.pkl")
+    with open(vis_pkl, "wb") as f:
+        pickle.dump(vis, f)
+    args = dict(parquet_path=parquet, overlap_min=6, overlap_max=35, interval=1, desired_count=count)
+    ref_dir, our_dir = str(tmp_path / "ref"), str(tmp_path / "ours")
+    os.makedirs(ref_dir), os.makedirs(our_dir)
+    random.seed(seed), np.random.seed(seed)
+    with quiet, np.errstate(all="ignore"):
+        if engine == "camera_movement":
+            mod.build_val_dataset(output_dir=ref_dir, scene_infos=rh, qtype=kw["qtype"], **args)
+        else:
+            mod.build_train_dataset(output_dir=ref_dir, scene_infos=rh, visibility_info_path=vis_pkl, warning_file=str(tmp_path / "rw.txt"),
+                                    max_points_per_pair=kw["max_points_per_pair"], **args)
+    want_after = (random.random(), float(np.random.random()))
+    cls = pair_engines.CameraMovementEngine if engine == "camera_movement" else pair_engines.VisualCorrespondenceCoorEngine
+    eng = cls(h, templates=t, rnd=random, cache=cache)
+    random.seed(seed), np.random.seed(seed)
+    with quiet:
+        if engine == "camera_movement":
+            eng.build_val_dataset(output_dir=our_dir, qtype=kw["qtype"], **args)
+        else:
+            eng.build_train_dataset(output_dir=our_dir, warning_file=str(tmp_path / "ow.txt"), max_points_per_pair=kw["max_points_per_pair"], **args)
+    assert (random.random(), float(np.random.random())) == want_after
+    (name,) = os.listdir(ref_dir)
+    want = [json.loads(l) for l in open(os.path.join(ref_dir, name))]
+    got = [json.loads(l) for l in open(os.path.join(our_dir, name))]
+    assert len(want) > 20 and got == want
