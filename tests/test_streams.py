@@ -224,3 +224,54 @@ def test_rigid_body_groups_match_reference(golden_tapvid, engines_golden):
         ref += np.where(ch > 0.01, ch, 0)
         prev = cur
     np.testing.assert_allclose(loss.cpu().numpy(), ref, rtol=1e-12, atol=1e-14)
+
+
+def test_coverage_search_differential_against_live_reference_cpu():
+    """40 random scenarios (object points along an axis, images seeing random subsets, up to 28 images so that the 25-image
+    random.sample cap fires too): the reference's BFS on union masks (SOCF:76-220, imported live when its checkout is mounted)
+    and this repo's BFS on per-image extents return the same dictionary from the same `random` state."""
+    import contextlib
+    import io
+    import json
+    import random
+    from multi_spatialmllm_b200 import coverage
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference checkout not mounted")
+    ref_shim.import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from spatial_engine.object_perception import single_object_coverage_finder as socf
+    rng = np.random.default_rng(11)
+    n_sol = 0
+    for case in range(40):
+        n_pts, n_img = int(rng.integers(50, 400)), int(rng.integers(1, 29))
+        pts = rng.uniform(-3, 3, (n_pts, 3))
+        obj = np.sort(rng.choice(n_pts, int(rng.integers(5, n_pts)), replace=False))
+        axis = int(rng.integers(0, 3))
+        target = float(np.ptp(pts[obj, axis]) * rng.choice([1.0, 1.0, 0.97, 1.2]))
+        tol = float(rng.choice([0.1, 0.3]))
+        images, vdict, lo, hi = [], {}, [], []
+        order = np.argsort(pts[:, axis])
+        for k in range(n_img):
+            img = f"{5 * k:05d}"
+            if rng.random() < 0.7:                                   # a window along the axis (what a camera sees), plus clutter
+                a = int(rng.integers(0, n_pts - 1))
+                seen = order[a:a + int(rng.integers(1, n_pts))]
+            else:
+                seen = rng.choice(n_pts, int(rng.integers(0, n_pts)), replace=False)
+            seen = np.sort(seen)
+            images.append(img)
+            vdict[f"s:image_to_points:{img}"] = json.dumps(seen.tolist())
+            vis_obj = np.intersect1d(seen, obj)
+            lo.append(pts[vis_obj, axis].min() if len(vis_obj) else np.inf)
+            hi.append(pts[vis_obj, axis].max() if len(vis_obj) else -np.inf)
+        random.seed(case)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = socf.find_minimal_combinations("s", pts, obj, images, vdict, axis, target, tol, max_images=4)
+        want_after = random.random()
+        random.seed(case)
+        got = coverage.find_minimal_combinations(images, lo, hi, target, tol, max_images=4)
+        assert {k: [tuple(c) for c in v] for k, v in got.items()} == {k: [tuple(c) for c in v] for k, v in want.items()}, case
+        assert random.random() == want_after, case
+        n_sol += sum(len(v) for v in got.values())
+    assert n_sol > 50
