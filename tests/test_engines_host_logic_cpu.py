@@ -388,3 +388,46 @@ def test_pair_engines_differential_against_live_reference_cpu(engine, seed, coun
     want = [json.loads(l) for l in open(os.path.join(ref_dir, name))]
     got = [json.loads(l) for l in open(os.path.join(our_dir, name))]
     assert len(want) > 20 and got == want
+
+
+@pytest.mark.parametrize("clip", [(31, 26, 54, 3, "tapvid3d_total_distance", 4, 0.7, 21), (32, 18, 40, 2, "tapvid3d_displacement_vector", 6, 0.2, 22),
+                                  (33, 40, 30, 1, "tapvid3d_total_distance", 2, 1.0, 23)])
+def test_tapvid_worker_differential_against_live_reference_cpu(clip, monkeypatch, tmp_path):
+    """Clips and seeds outside the goldens: the unmodified TwoFrameVideoQAEngine.generate_qa_training_single_scene (when the
+    checkout is mounted) against this repo's worker over oracle answers — same samples, text and RNG position."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference checkout not mounted")
+    import contextlib
+    from multi_spatialmllm_b200 import streams, tapvid
+    gen = _load(os.path.join(ROOT, "tests", "golden", "make_golden_tapvid_sampling.py"), "_golden_tapvid_cpu")
+    ref_shim.import_reference()
+    quiet = contextlib.redirect_stdout(open(os.devnull, "w"))
+    with quiet:
+        from spatial_engine.object_movement import single_object_movement_engine_coord as om
+    vs, T, N, G, qt, npg, ratio, rs = clip
+    v = gen.make_clip(vs, T, N, G)
+    path = str(tmp_path / f"{v.video_id}.npz")
+    gen.write_npz(path, v)
+    eng = om.TwoFrameVideoQAEngine(qt, "adt")
+    eng.task_description, eng.question_templates, eng.answer_templates = (gen.TEMPLATES["task"], gen.TEMPLATES["questions"],
+                                                                         gen.TEMPLATES["answers"])
+    random.seed(rs)
+    with quiet, np.errstate(all="ignore"):
+        want = eng.generate_qa_training_single_scene(path, npoints_per_group=npg, npairs_per_bin=1e8,
+                                                     img_output_dir=str(tmp_path / "img"), augment=True, augment_ratio=ratio)
+    want_after = random.random()
+    monkeypatch.setattr(tapvid, "DeviceVideo", OracleVideo)
+    monkeypatch.setattr(tapvid, "all_pair_distances", _oracle_all_pair_distances)
+    video = {"images_jpeg_bytes": None, "fx_fy_cx_cy": v.fxfycxcy, "tracks_XYZ": v.tracks_xyz, "visibility": v.visibility,
+             "extrinsics_w2c": v.w2c}
+    random.seed(rs)
+    got = tapvid.generate_video_samples(video, v.video_id, qt, npoints_per_group=npg, npairs_per_bin=1e8, image_hw=(36, 64),
+                                        augment=True, augment_ratio=ratio,
+                                        templates=streams.Templates({f"object_movement:{qt}": gen.TEMPLATES}), rnd=random)
+    assert random.random() == want_after
+    got, want = json.loads(json.dumps(got)), json.loads(json.dumps(want))
+    assert [e["id"] for e in got] == [e["id"] for e in want] and len(want) > 0
+    for e, w in zip(got, want):
+        for key in ("gt_value", "image", "conversations", "p1", "p2", "point_moving", "cam_moving", "height_list", "width_list"):
+            assert e[key] == w[key], (e["id"], key)
