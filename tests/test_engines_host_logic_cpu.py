@@ -431,3 +431,55 @@ def test_tapvid_worker_differential_against_live_reference_cpu(clip, monkeypatch
     for e, w in zip(got, want):
         for key in ("gt_value", "image", "conversations", "p1", "p2", "point_moving", "cam_moving", "height_list", "width_list"):
             assert e[key] == w[key], (e["id"], key)
+
+
+@pytest.mark.parametrize("key,module,cls_name,n_max,npp,seed", [
+    ("depth_estimation", "depth_estimation_coor_engine", "DepthEstimationCoorQAEngine", 14, 3, 41),
+    ("depth_comparison", "depth_comparison_coor_engine", "DepthComparisonCoorQAEngine", 40, 1, 42)])
+def test_depth_engines_differential_against_live_reference_cpu(key, module, cls_name, n_max, npp, seed, tmp_path, monkeypatch):
+    """Seeds / sizes outside the goldens: the unmodified depth engine (live, when the checkout is mounted) against this repo's
+    engine over oracle answers."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference checkout not mounted")
+    import contextlib
+    import io
+    import pickle
+    from multi_spatialmllm_b200 import engines
+    gen = _load(os.path.join(ROOT, "tests", "golden", "make_golden_depth_engines.py"), "_golden_depth_cpu")
+    ref = ref_shim.import_reference()
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    scenes = gen.scenes_from_fixture()
+    root = str(tmp_path / "data" / "scannet")
+    info = ref_layout.write_split(scenes, root, name="scenes_val_info_i_D5.pkl")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)                                       # the reference engines use the relative default roots
+    try:
+        with quiet, np.errstate(all="ignore"):
+            rh = ref.info_handler.SceneInfoHandler(info)
+            vis = {s.scene_id: ref.mvi.process_scene(s.scene_id, rh, str(tmp_path / "w.txt"))[1] for s in scenes}
+            pkl = os.path.join(root, "scannet_instance_data", "val_visibility_info_D5.pkl")
+            with open(pkl, "wb") as f:
+                pickle.dump(vis, f)
+            ref.mvi.convert_pkl_to_parquet(pkl)
+            mod = __import__(f"spatial_engine.depth_perception.{module}", fromlist=[cls_name])
+            reng = getattr(mod, cls_name)(scene_info_path=info, version_num="v1_0", all_max_samples=n_max, image_output_dir=None,
+                                          visibility_info_path=pkl.replace(".pkl", ".parquet"), max_n_points_per_image=npp,
+                                          warning_file=str(tmp_path / "warn.txt"))
+            t = gen.TEMPLATES[key]
+            reng.task_description, reng.templates = t["task"], {k: v for k, v in t.items() if k != "task"}
+            random.seed(seed)
+            want = reng.generate_qa_training_data(str(tmp_path / "ref_out"), save_file=False)
+        want_after = random.random()
+    finally:
+        os.chdir(cwd)
+    OracleSession.scenes = {s.scene_id: s for s in scenes}
+    monkeypatch.setattr(engines, "SceneSession", OracleSession)
+    eng = getattr(engines, cls_name)(info, "v1_0", n_max, None, None, npp, str(tmp_path / "warn2.txt"),
+                                     posed_images_root=os.path.join(root, "posed_images"),
+                                     instance_data_root=os.path.join(root, "scannet_instance_data"), templates=t, rnd=random)
+    random.seed(seed)
+    with quiet, np.errstate(all="ignore"):
+        got = eng.generate_qa_training_data(str(tmp_path / "our_out"), save_file=False)
+    assert random.random() == want_after
+    assert json.loads(json.dumps(got)) == json.loads(json.dumps(want)) and len(want) >= min(n_max, 10)
