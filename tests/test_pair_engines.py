@@ -411,3 +411,32 @@ def test_sample_dataframe_differential_against_live_reference_cpu():
             got = pair_engines.sample_dataframe(df, n_all, n_zero, lo, hi, step)
         assert [int(v) for v in got["row"]] == [int(v) for v in want["row"]], (case, rows, lo, hi, step, n_all, n_zero)
         assert float(np.random.random()) == want_after, case
+
+
+def test_scene_cache_evicts_least_recently_used_cpu(monkeypatch):
+    """SceneCache keeps scenes resident up to its byte budget and drops the least recently used first."""
+    import torch
+    from multi_spatialmllm_b200 import pair_engines, tables
+    loads = []
+
+    class FakeScene:
+        def __init__(self, nbytes):
+            self.pts, self.depth, self.mask = torch.zeros(nbytes // 2, dtype=torch.uint8), torch.zeros(nbytes // 2, dtype=torch.uint8), None
+
+        def project_visibility(self):
+            self.mask = torch.zeros(16, dtype=torch.int32)
+
+    def fake_load(scene_infos, scene_id, device="cuda:0"):
+        loads.append(scene_id)
+        return FakeScene(1000), ["00000", "00005"]
+
+    monkeypatch.setattr(tables, "device_scene_from_handler", fake_load)
+    cache = pair_engines.SceneCache(None, device="cpu", budget_bytes=2300)          # two scenes of ~1064 B fit, three do not
+    a, rows = cache.get("a")
+    assert rows == {"00000": 0, "00005": 1} and a.mask is not None
+    cache.get("b")
+    assert cache.get("a")[0] is a and loads == ["a", "b"]                            # a hit, and "a" is now the most recent
+    cache.get("c")                                                                   # evicts "b", the least recently used
+    assert cache.get("a")[0] is a and loads == ["a", "b", "c"]
+    cache.get("b")
+    assert loads == ["a", "b", "c", "b"]
