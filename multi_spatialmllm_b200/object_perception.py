@@ -160,6 +160,16 @@ def merge_split(split, base_dir, output_dir):
     return out
 
 
+def merge_main(argv=None):
+    """merge_object_coverage.py:85-97: merge the shard files of both splits under the reference's default directories."""
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--train_base", default="training_data/object_perception")
+    ap.add_argument("--val_base", default="evaluation_data/object_perception")
+    a = ap.parse_args(argv)
+    return {"train": merge_split("train", a.train_base, a.train_base), "val": merge_split("val", a.val_base, a.val_base)}
+
+
 # ------------------------------------------------------------------------------------------------
 # L3 samples
 # ------------------------------------------------------------------------------------------------

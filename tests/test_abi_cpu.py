@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -66,3 +67,17 @@ def test_engine_refuses_to_run_without_cuda():
     s = synth.make_scene(0, 100, 1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         engine.DeviceScene(s.points, s.K, s.c2w)
+
+
+def test_package_command_table_cpu(capsys):
+    """`python -m multi_spatialmllm_b200 <reference script>`: every reference script name resolves to a callable entry point."""
+    import importlib
+    from multi_spatialmllm_b200 import __main__ as cli
+    assert cli.main([]) == 0 and "calculate_frames_relations" in capsys.readouterr().out
+    assert cli.main(["no_such_script"]) == 2
+    for name, (module, fn, lead, ref) in cli.COMMANDS.items():
+        mod = importlib.import_module(f"multi_spatialmllm_b200.{module}")
+        assert callable(getattr(mod, fn)), name
+    with pytest.raises(SystemExit) as e:                      # argparse --help of a dispatched command exits 0
+        cli.main(["visual_correspondence_qa_engine_coor_2_coor.py", "--help"])
+    assert e.value.code == 0
