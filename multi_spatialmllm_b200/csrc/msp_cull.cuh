@@ -37,7 +37,7 @@ constexpr int kCullPtsPerLane = 8;                             // 8 groups of 32
 constexpr int kCullWarpPoints = 32 * kCullPtsPerLane;          // 256
 constexpr int kCullTilePoints = kCullWarps * kCullWarpPoints;  // 2048
 #ifndef MSP_CULL_FRAMES
-#define MSP_CULL_FRAMES 64
+#define MSP_CULL_FRAMES 48
 #endif
 constexpr int kCullFramesPerCta = MSP_CULL_FRAMES;
 constexpr int kCullMaxObjects = 63;
@@ -51,16 +51,16 @@ constexpr int kCullMaxObjects = 63;
 #define MSP_CULL_BOX_SMEM 1    // 1: the warp's 8 group boxes live in SMEM (2 LDS.128 per frame) instead of 6 registers, two of which spilled
 #endif
 #ifndef MSP_CULL_DEFER_EXACT
-#define MSP_CULL_DEFER_EXACT 0     // 1 (visibility mode): lanes queued for the exact float64 path are collected per warp ACROSS frames and
+#define MSP_CULL_DEFER_EXACT 1     // 1 (visibility mode): lanes queued for the exact float64 path are collected per warp ACROSS frames and
                                    // evaluated 32 at a time, OR-ing the few visible bits into the already stored mask words, instead of
                                    // running the ~200-instruction exact path for one or two lanes in ~15 % of the warp-frames
                                    // (end of round 1: -10 % on a 200 k x 512 scene with bit-identical masks and counts,
-                                   // profiles/variant_check_r1.txt; not yet through the whole GPU suite, hence still off)
+                                   // profiles/variant_check_r1.txt; round 2: whole -m gpu suite green on it, shipped on)
 #endif
 #ifndef MSP_CULL_STRIDED_GROUPS
-#define MSP_CULL_STRIDED_GROUPS 0  // 1: warp w owns the tile's groups w, w+8, w+16, ... instead of 8 consecutive ones, so that the eight
+#define MSP_CULL_STRIDED_GROUPS 1  // 1: warp w owns the tile's groups w, w+8, w+16, ... instead of 8 consecutive ones, so that the eight
                                    // warps of a CTA sample the tile's extent alike and finish their frames together (end of round 1:
-                                   // -2.6 %, bit-identical output, profiles/variant_check_r1.txt; not yet through the whole GPU suite)
+                                   // -2.6 %, bit-identical output, profiles/variant_check_r1.txt; round 2: whole -m gpu suite green, shipped on)
 #endif
 #if MSP_CULL_STRIDED_GROUPS
 #define MSP_CULL_GROUP(warp, j) ((j) * kCullWarps + (warp))

@@ -776,11 +776,9 @@ static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool m
 #define MSP_CULL_LAUNCH(DT, CNT)                                                                             \
   {                                                                                                          \
     constexpr int smem = kCullTilePoints * PtTraits<DT>::kBytes;                                             \
-    static bool attr_set = false;                                                                            \
-    if (!attr_set) {                                                                                         \
-      cudaFuncSetAttribute(k_frame_cull<DT, MODE, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
-      attr_set = true;                                                                                       \
-    }                                                                                                        \
+    /* the attribute is per device and this library may drive several: set it on every call (cheap, thread-safe) */ \
+    if (cudaFuncSetAttribute(k_frame_cull<DT, MODE, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) \
+      return check_launch("k_frame_cull(cudaFuncSetAttribute)");                                            \
     k_frame_cull<DT, MODE, CNT><<<grid, kCullThreads, smem, s>>>(c);                                         \
   }
 #define MSP_CULL(DT)                                      \
