@@ -1,0 +1,1022 @@
+// K1 fast path, second generation ("v9"): msp_project_visibility / msp_project_visibility_objects with standard intrinsics.
+//
+// Same arithmetic contract and the same float32-decision-with-proven-bounds scheme as msp_cull.cuh (read its header comment
+// first: forms I0, Q1, I1, Q3, Z re-centred on the tile centre, bounds B / B_Z, pixel guard band ct1 * rcp(Z) + ct0, depth
+// guard 6u d + B_Z, everything uncertain goes to the exact float64 reference-order code).  What changed is the shape of the
+// work, driven by the round-1 ncu capture (353 M warp instructions per 2 000-frame launch, 60 % issue utilisation: the kernel
+// is instruction-issue bound, not HBM bound):
+//
+//   * k_cull_prepare (one launch per call, ~2 % of K1's time) does everything that only depends on the POINTS once instead
+//     of once per (tile, frame chunk): tile centre, re-centred float32 coordinates, super-group boxes, extents and the
+//     per-tile instance-id table.  Its output (CullTilePrep, 27 KB per 2 048-point tile) is what the main kernel stages
+//     into shared memory with ONE bulk async copy (TMA engine, UBLKCP) — no reductions, no re-centring in the hot kernel.
+//   * the unit of evaluation is a SUPER-GROUP of 64 consecutive points, two per lane, stored as float2 (lo, hi): the whole
+//     float32 projection runs on Blackwell's packed FFMA2 / FADD2 / FMUL2 (fma.rn.f32x2 ...), which take one issue slot
+//     for two points (measured: profiles/r2/ubench_f32x2.txt — half the FMA-pipe rate, but the pipe was only 23 % busy).
+//     Frame coefficients are stored duplicated (c, c) so that they are packed operands straight out of shared memory.
+//   * group classification runs with lane = FRAME: one pass tests a super-group box against the four half-spaces of 32
+//     frames at once (no ballot, no per-frame head), leaves a 4-bit candidate mask per (warp, frame) in a register, and the
+//     lanes write the all-zero mask words of their non-candidate (frame, super-group)s directly.  The main loop then only
+//     visits frames that have a candidate (ffs over a ballot), in ascending frame order (depth-map locality in L1/L2).
+//   * each candidate super-group's two mask words are stored by lane 0 straight from the ballots (no word shuffling);
+//   * uncertain lanes are queued per warp ACROSS frames and the exact float64 path runs on 32 of them at a time, OR-ing
+//     visible bits into the stored words (the validated round-1 "deferred exact" variant, now the only exact path — a
+//     non-standard frame simply queues every lane and becomes the all-float64 kernel at full lane utilisation);
+//   * fused per-(frame, object) counting works for ANY number of objects: a tile of 2 048 consecutive points touches few
+//     instances, so the prepare pass gives each tile a 15-entry local id table; counts are accumulated per (frame, local
+//     slot) in 2 KB of shared memory (was 8 KB for <= 63 global ids) and flushed with one atomic per non-zero counter.  Ids
+//     that do not fit the table (> 15 distinct in one tile, e.g. shuffled clouds) are counted with global atomics.
+//
+// Bit-identical to k_frame_loop (all-float64) and to the round-1 kernel by construction: a float32 decision is only taken
+// when the bounds prove it; the packed operations are IEEE single roundings per half in the same association order as the
+// scalar code (fl(a0 x' + fl(a1 y' + fl(a2 z' + d')))), the pixel value I0 * rcp(Z) is now used as the EXACT product
+// inside an FMA (one rounding fewer than the bound allows for).
+#pragma once
+
+#include <stddef.h>
+
+#include "msp_cull.cuh"
+#include "msp_device.cuh"
+
+namespace msp {
+
+constexpr int kC9Threads = 256;
+constexpr int kC9Warps = kC9Threads / 32;
+constexpr int kC9SgPerWarp = 4;                                   // super-groups (64 points, two per lane) per warp
+constexpr int kC9TileSgs = kC9Warps * kC9SgPerWarp;               // 32
+constexpr int kC9TilePoints = kC9TileSgs * 64;                    // 2048
+constexpr int kC9TileWords = kC9TilePoints / 32;                  // 64 mask words per tile and frame
+#ifndef MSP_C9_FRAMES
+#define MSP_C9_FRAMES 32
+#endif
+constexpr int kC9Frames = MSP_C9_FRAMES;                          // frames per CTA, a multiple of 32
+constexpr int kC9Rounds = kC9Frames / 32;
+static_assert(kC9Frames % 32 == 0 && kC9Frames <= 256, "frames per CTA");
+constexpr int kC9Slots = 16;                                      // local instance-id slots per tile (slot 15 is never used: 15 ids)
+constexpr uint32_t kC9DeferCap = 288;                             // < 32 left over + at most 4 x 64 appended per frame
+#ifndef MSP_C9_MINBLOCKS
+#define MSP_C9_MINBLOCKS 4
+#endif
+#ifndef MSP_C9_STRIDED
+#define MSP_C9_STRIDED 1       // 1: warp w owns super-groups w, w+8, w+16, w+24 (even work per warp), 0: 4w .. 4w+3
+#endif
+#ifndef MSP_C9_MASK0_REG
+#define MSP_C9_MASK0_REG 1
+#endif
+#ifndef MSP_C9_LOOP
+#define MSP_C9_LOOP 3       // main loop: 3 pipelined by one super-group within a frame, 0 one super-group at a time, 2 two at a time with the gathers of a pair in flight together
+#endif                      //   (measured slower: at 64 registers the pending state spills, profiles/r2/k1_tuning.md)
+#ifndef MSP_C9_PFL2
+#define MSP_C9_PFL2 0       // > 0: every warp prefetches its rows of the tile's projected bounding box in the depth map of the frame
+#endif                      //   MSP_C9_PFL2 candidate-frames ahead into L2 (prefetch.global.L2), so the gathers find it there
+#ifndef MSP_C9_PF
+#define MSP_C9_PF 0         // 1: stage 1 only PREFETCHES the two depth pixels into L1 (CCTL.E.PF1, no scoreboard) and stage 2 loads them
+#endif
+#ifndef MSP_C9_COEF_PER_SG
+#define MSP_C9_COEF_PER_SG 1   // 1: the 12 packed frame coefficients are re-read from shared memory for every super-group (fewer live registers:
+                               //    without it the pending gather state of the pipelined loop spills; measured 0.470 vs 0.535 ms)
+#endif
+#if MSP_C9_STRIDED
+#define MSP_C9_SG(warp, k) ((warp) + kC9Warps * (k))
+#else
+#define MSP_C9_SG(warp, k) ((warp) * kC9SgPerWarp + (k))
+#endif
+
+constexpr uint8_t kC9SlotNone = 0xFE;      // no object (id 0, id out of range, slot beyond the cloud)
+constexpr uint8_t kC9SlotOverflow = 0xFD;  // the id is not in the tile's table: look it up in inst[] and count with a global atomic
+constexpr uint8_t kC9SlotMixed = 0xFF;     // (super-group only) its points carry different ids: per-lane path
+
+struct __align__(16) CullTilePrep {
+  float2 pts[kC9TileSgs][3][32];  // [sg][x|y|z][lane] = (point 64 sg + lane, point 64 sg + 32 + lane) re-centred; NaN = empty slot
+  float4 box[kC9TileSgs][2];      // [sg] (cx,cy,cz,-), (hx,hy,hz,-): box of the super-group's re-centred points, half sizes rounded up
+  float centre[3];                // tile centre (float32, any finite value is correct)
+  float ext[3];                   // max |x'|, |y'|, |z'| over the tile
+  float pad0[2];
+  uint16_t slot_id[kC9Slots];     // local slot -> instance id (0 = unused)
+  uint8_t sg_slot[kC9TileSgs];    // 0..14 all points share the id in that slot, kC9SlotNone, or kC9SlotMixed
+  uint8_t pt_slot[kC9TilePoints]; // per point: 0..14, kC9SlotNone or kC9SlotOverflow
+};
+static_assert(sizeof(CullTilePrep) % 16 == 0 && offsetof(CullTilePrep, pt_slot) % 16 == 0, "bulk copy sizes");
+
+struct __align__(16) C9Frame {    // per (tile, frame); 176 bytes = 11 x 16 so that lane = frame LDS.128 accesses are conflict-free
+  float2 a0[4];                   // I0 = sx (fx X + cx Z) as {x, y, z, d'} relative to the tile centre, each value twice (packed operand)
+  float2 a2[4];                   // I1
+  float2 az[4];                   // Z
+  float q1[4];                    // Q1 = dw Z - I0 (classification only)
+  float q3[4];                    // Q3 = dh Z - I1
+  float2 ct1, hct0, Bz;           // pixel guard band dt = ct1 rcp(Z) + ct0 as (ct1, 0.5 - ct0); depth-form bound; duplicated
+  float B, B2;                    // common bound of the four in-image forms, and twice that
+  unsigned long long dm_biased;   // depth map byte address - 2 * 0x4B000000 (gather index = as_uint(di + 2^23))
+  int std_frame;                  // bottom row of w2c is exactly [0,0,0,1]
+  uint32_t bbox;                  // depth-map window the tile can project into: row0 | rows << 9 | line0 << 18 | lines << 22 (128-byte lines), 0 = none
+};
+static_assert(sizeof(C9Frame) == 176, "C9Frame layout");
+
+// ---- packed float32x2 arithmetic (one issue slot for two IEEE single operations; FFMA2 / FADD2 / FMUL2 in SASS) ----------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 lds64(uint32_t addr) {
+  f32x2 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds128(uint32_t addr, f32x2& a, f32x2& b) {
+  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
+__device__ __forceinline__ void red_smem_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// ================================================================================================================
+// prepare pass: everything that depends on the points only.  One CTA per 2 048-point tile, warp w owns super-groups 4w..4w+3.
+// ================================================================================================================
+template <int DT>
+__global__ void __launch_bounds__(kC9Threads) k_cull_prepare(const void* __restrict__ pts, int64_t n,
+                                                             const uint16_t* __restrict__ inst, int32_t n_objects,
+                                                             CullTilePrep* __restrict__ out) {
+  __shared__ int s_red[9];           // ordered-int min xyz, max xyz, then uint max |x'|,|y'|,|z'|
+  __shared__ uint32_t s_ids[kC9Slots];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * kC9TilePoints;
+  const int cnt = (int)min((int64_t)kC9TilePoints, n - base);
+  CullTilePrep& o = out[blockIdx.x];
+  const unsigned char* gp = static_cast<const unsigned char*>(pts) + base * PtTraits<DT>::kBytes;
+  if (tid == 0) {
+    s_red[0] = s_red[1] = s_red[2] = 0x7fffffff;
+    s_red[3] = s_red[4] = s_red[5] = (int)0x80000000;
+    s_red[6] = s_red[7] = s_red[8] = 0;
+  }
+  if (tid < kC9Slots) s_ids[tid] = 0u;
+  __syncthreads();
+
+  const float qnan = __int_as_float(0x7fc00000), finf = __int_as_float(0x7f800000);
+  float X[kC9SgPerWarp][2], Y[kC9SgPerWarp][2], Z[kC9SgPerWarp][2];
+  {
+    float lx = finf, ly = finf, lz = finf, hx = -finf, hy = -finf, hz = -finf;
+#pragma unroll
+    for (int k = 0; k < kC9SgPerWarp; ++k)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int idx = (warp * kC9SgPerWarp + k) * 64 + 32 * h + lane;
+        X[k][h] = Y[k][h] = Z[k][h] = qnan;  // slots beyond the cloud and non-finite points: every comparison on them is false
+        if (idx < cnt) {
+          float x, y, z;
+          load_point_f32<DT>(gp, idx, x, y, z);
+          if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            X[k][h] = x, Y[k][h] = y, Z[k][h] = z;
+            lx = fminf(lx, x), ly = fminf(ly, y), lz = fminf(lz, z);
+            hx = fmaxf(hx, x), hy = fmaxf(hy, y), hz = fmaxf(hz, z);
+          }
+        }
+      }
+    const int ox0 = __reduce_min_sync(0xffffffffu, f2ord(lx)), ox1 = __reduce_max_sync(0xffffffffu, f2ord(hx));
+    const int oy0 = __reduce_min_sync(0xffffffffu, f2ord(ly)), oy1 = __reduce_max_sync(0xffffffffu, f2ord(hy));
+    const int oz0 = __reduce_min_sync(0xffffffffu, f2ord(lz)), oz1 = __reduce_max_sync(0xffffffffu, f2ord(hz));
+    if (lane == 0) {
+      atomicMin(&s_red[0], ox0), atomicMin(&s_red[1], oy0), atomicMin(&s_red[2], oz0);
+      atomicMax(&s_red[3], ox1), atomicMax(&s_red[4], oy1), atomicMax(&s_red[5], oz1);
+    }
+  }
+  __syncthreads();
+  float tcx = 0.5f * (ord2f(s_red[0]) + ord2f(s_red[3])), tcy = 0.5f * (ord2f(s_red[1]) + ord2f(s_red[4])),
+        tcz = 0.5f * (ord2f(s_red[2]) + ord2f(s_red[5]));
+  if (!isfinite(tcx) || !isfinite(tcy) || !isfinite(tcz)) tcx = tcy = tcz = 0.f;  // empty tile; any finite centre is correct
+
+  float ex = 0.f, ey = 0.f, ez = 0.f;
+#pragma unroll
+  for (int k = 0; k < kC9SgPerWarp; ++k) {
+    const int sg = warp * kC9SgPerWarp + k;
+    float lx = finf, ly = finf, lz = finf, hx = -finf, hy = -finf, hz = -finf;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (DT == 2) {
+        // float64 inputs: subtract the centre in float64 and round ONCE, so that the error of x' is u |x'| and not u |x|
+        if (X[k][h] == X[k][h]) {
+          const int idx = sg * 64 + 32 * h + lane;
+          double x64, y64, z64;
+          PtTraits<DT>::load(gp, idx, x64, y64, z64);
+          X[k][h] = __double2float_rn(x64 - (double)tcx);
+          Y[k][h] = __double2float_rn(y64 - (double)tcy);
+          Z[k][h] = __double2float_rn(z64 - (double)tcz);
+        }
+      } else {
+        X[k][h] -= tcx, Y[k][h] -= tcy, Z[k][h] -= tcz;  // NaN stays NaN
+      }
+      const float x = X[k][h], y = Y[k][h], z = Z[k][h];
+      if (x == x) {
+        ex = fmaxf(ex, fabsf(x)), ey = fmaxf(ey, fabsf(y)), ez = fmaxf(ez, fabsf(z));
+        lx = fminf(lx, x), ly = fminf(ly, y), lz = fminf(lz, z);
+        hx = fmaxf(hx, x), hy = fmaxf(hy, y), hz = fmaxf(hz, z);
+      }
+    }
+    const float gx0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lx))), gx1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hx)));
+    const float gy0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(ly))), gy1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hy)));
+    const float gz0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lz))), gz1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hz)));
+    if (lane == 0) {
+      // centre / half size with the half size rounded up so that [c-h, c+h] certainly contains the super-group's x'
+      const float k1 = 1.0f + 2.384185791015625e-07f, k2 = 4.76837158203125e-07f;  // 1+2^-22, 2^-21
+      const float bcx = 0.5f * (gx0 + gx1), bcy = 0.5f * (gy0 + gy1), bcz = 0.5f * (gz0 + gz1);
+      const float bhx = __fmaf_ru(0.5f * (gx1 - gx0), k1, k2 * fmaxf(fabsf(gx0), fabsf(gx1)));
+      const float bhy = __fmaf_ru(0.5f * (gy1 - gy0), k1, k2 * fmaxf(fabsf(gy0), fabsf(gy1)));
+      const float bhz = __fmaf_ru(0.5f * (gz1 - gz0), k1, k2 * fmaxf(fabsf(gz0), fabsf(gz1)));
+      // an empty super-group has inf - inf = NaN in its centre: every test on it is false, it is never a candidate
+      o.box[sg][0] = make_float4(bcx, bcy, bcz, 0.f);
+      o.box[sg][1] = make_float4(bhx, bhy, bhz, 0.f);
+    }
+    o.pts[sg][0][lane] = make_float2(X[k][0], X[k][1]);
+    o.pts[sg][1][lane] = make_float2(Y[k][0], Y[k][1]);
+    o.pts[sg][2][lane] = make_float2(Z[k][0], Z[k][1]);
+  }
+  {
+    const uint32_t ux = __reduce_max_sync(0xffffffffu, __float_as_uint(ex));
+    const uint32_t uy = __reduce_max_sync(0xffffffffu, __float_as_uint(ey));
+    const uint32_t uz = __reduce_max_sync(0xffffffffu, __float_as_uint(ez));
+    if (lane == 0) atomicMax(&s_red[6], (int)ux), atomicMax(&s_red[7], (int)uy), atomicMax(&s_red[8], (int)uz);
+  }
+
+  // ---- instance ids: the tile's table of distinct ids (first come, first served) and every point's local slot
+  uint32_t id[kC9SgPerWarp][2];
+  if (inst != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kC9SgPerWarp; ++k)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int idx = (warp * kC9SgPerWarp + k) * 64 + 32 * h + lane;
+        uint32_t v = (idx < cnt) ? (uint32_t)__ldg(inst + base + idx) : 0u;
+        if (v > (uint32_t)n_objects) v = 0u;
+        id[k][h] = v;
+        const uint32_t peers = __match_any_sync(0xffffffffu, v);
+        if (v != 0u && lane == __ffs(peers) - 1) {
+          for (int s = 0; s < kC9Slots - 1; ++s) {
+            const uint32_t old = atomicCAS(&s_ids[s], 0u, v);
+            if (old == 0u || old == v) break;
+          }
+        }
+      }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    o.centre[0] = tcx, o.centre[1] = tcy, o.centre[2] = tcz;
+    o.ext[0] = __int_as_float(s_red[6]), o.ext[1] = __int_as_float(s_red[7]), o.ext[2] = __int_as_float(s_red[8]);
+    o.pad0[0] = o.pad0[1] = 0.f;
+  }
+  if (tid < kC9Slots) o.slot_id[tid] = (inst != nullptr) ? (uint16_t)s_ids[tid] : (uint16_t)0;
+  if (inst != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kC9SgPerWarp; ++k) {
+      const int sg = warp * kC9SgPerWarp + k;
+      uint32_t sl[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t v = id[k][h];
+        uint32_t s = kC9SlotNone;
+        if (v != 0u) {
+          s = kC9SlotOverflow;
+          for (int t = 0; t < kC9Slots - 1; ++t)
+            if (s_ids[t] == v) s = (uint32_t)t;
+        }
+        sl[h] = s;
+        o.pt_slot[sg * 64 + 32 * h + lane] = (uint8_t)s;
+      }
+      // uniform super-group: every point INSIDE the cloud carries the same id (slots beyond it never become visible)
+      const uint32_t first = __shfl_sync(0xffffffffu, id[k][0], 0);
+      const uint32_t first_slot = __shfl_sync(0xffffffffu, sl[0], 0);
+      const int i0 = sg * 64 + lane, i1 = i0 + 32;
+      const bool same = __all_sync(0xffffffffu, (id[k][0] == first || i0 >= cnt) && (id[k][1] == first || i1 >= cnt));
+      if (lane == 0) o.sg_slot[sg] = (uint8_t)((same && first_slot != kC9SlotOverflow) ? first_slot : kC9SlotMixed);
+    }
+  } else {
+    if (tid < kC9TileSgs) o.sg_slot[tid] = kC9SlotNone;
+  }
+}
+
+// ================================================================================================================
+// per-(tile, frame) float32 forms and rigorous error bounds, float64 arithmetic (identical to the round-1 kernel)
+// ================================================================================================================
+__device__ __forceinline__ void c9_frame_consts(const double* __restrict__ w, const Intrinsics& K, const ImageGeom& g,
+                                                const float* __restrict__ centre, const float* __restrict__ extf,
+                                                const uint16_t* depth_map, C9Frame& c) {
+  const float finf = __int_as_float(0x7f800000);
+  const double kUp = 1.0 + 2.4e-07;  // extents: cover the rounding of x' itself and of float64 inputs
+  const double ext[3] = {(double)extf[0] * kUp, (double)extf[1] * kUp, (double)extf[2] * kUp};
+  const double tc[3] = {(double)centre[0], (double)centre[1], (double)centre[2]};
+  const double fx = K.k[0], cx = K.k[2], fy = K.k[5], cy = K.k[6];
+  const double sx = g.sx, sy = g.sy, dw = (double)g.depth_w, dh = (double)g.depth_h;
+  double A[5][4], M[5], mag[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    mag[r] = fabs(w[4 * r]) * (fabs(tc[0]) + ext[0]) + fabs(w[4 * r + 1]) * (fabs(tc[1]) + ext[1]) +
+             fabs(w[4 * r + 2]) * (fabs(tc[2]) + ext[2]) + fabs(w[4 * r + 3]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    A[0][k] = sx * (fx * w[k] + cx * w[8 + k]);
+    A[2][k] = sy * (fy * w[4 + k] + cy * w[8 + k]);
+    A[4][k] = w[8 + k];
+    A[1][k] = dw * w[8 + k] - A[0][k];
+    A[3][k] = dh * w[8 + k] - A[2][k];
+  }
+  M[0] = fabs(sx) * (fabs(fx) * mag[0] + fabs(cx) * mag[2]);
+  M[2] = fabs(sy) * (fabs(fy) * mag[1] + fabs(cy) * mag[2]);
+  M[4] = mag[2];
+  M[1] = dw * mag[2] + M[0];
+  M[3] = dh * mag[2] + M[2];
+  const double u = 5.9604644775390625e-08, tiny = 1.4210854715202004e-14;  // 2^-24, 2^-46
+  double Bf[5];
+  float co[5][4];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const double dprime = A[q][0] * tc[0] + A[q][1] * tc[1] + A[q][2] * tc[2] + A[q][3];
+    const double Aext = fabs(A[q][0]) * ext[0] + fabs(A[q][1]) * ext[1] + fabs(A[q][2]) * ext[2];
+    Bf[q] = 8.0 * u * (Aext + fabs(dprime)) + tiny * M[q];
+    co[q][0] = __double2float_rn(A[q][0]), co[q][1] = __double2float_rn(A[q][1]), co[q][2] = __double2float_rn(A[q][2]);
+    co[q][3] = __double2float_rn(dprime);
+  }
+  // Q1 and Q3 are *derived* in the point loop as fl(dw Z^ - I0^): their error is B_I0 + dw B_Z + one rounding
+  const double bq1 = 1.01 * (Bf[0] + dw * Bf[4]) + 0.13 * Bf[1];
+  const double bq3 = 1.01 * (Bf[2] + dh * Bf[4]) + 0.13 * Bf[3];
+  const double B = fmax(fmax(Bf[0], Bf[2]), fmax(fmax(Bf[1], Bf[3]), fmax(bq1, bq3)));
+  float Bf32 = __double2float_ru(B);
+  const float ct1 = __double2float_ru(1.01 * fmax(Bf[0] + dw * Bf[4], Bf[2] + dh * Bf[4]));
+  const float ct0 = __double2float_ru(8.0 * u * fmax(dw, dh) + 1e-9);
+  const float Bz = __double2float_ru(Bf[4]);
+  c.std_frame = (w[12] == 0.0) && (w[13] == 0.0) && (w[14] == 0.0) && (w[15] == 1.0);
+  if (!c.std_frame && isfinite(B)) {
+    // perspective row present: the forms are not the image-plane tests — every point goes to the exact path
+#pragma unroll
+    for (int q = 0; q < 4; ++q) co[q][0] = co[q][1] = co[q][2] = co[q][3] = 0.f;
+    Bf32 = finf;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    c.a0[k] = make_float2(co[0][k], co[0][k]);
+    c.a2[k] = make_float2(co[2][k], co[2][k]);
+    c.az[k] = make_float2(co[4][k], co[4][k]);
+    c.q1[k] = co[1][k];
+    c.q3[k] = co[3][k];
+  }
+  c.ct1 = make_float2(ct1, ct1);
+  c.hct0 = make_float2(0.5f - ct0, 0.5f - ct0);
+  c.Bz = make_float2(Bz, Bz);
+  c.B = Bf32;
+  c.B2 = Bf32 + Bf32;
+  c.dm_biased = (unsigned long long)depth_map - 2ull * 0x4B000000ull;
+  // conservative window of depth pixels this tile can land in (prefetch hint only: any value is correct).  Over the tile,
+  // form q stays within dprime +- Aext and Z within [zmin, zmax]; pixel = I / Z.
+  c.bbox = 0u;
+  {
+    const double e0 = fabs(A[0][0]) * ext[0] + fabs(A[0][1]) * ext[1] + fabs(A[0][2]) * ext[2];
+    const double e2 = fabs(A[2][0]) * ext[0] + fabs(A[2][1]) * ext[1] + fabs(A[2][2]) * ext[2];
+    const double e4 = fabs(A[4][0]) * ext[0] + fabs(A[4][1]) * ext[1] + fabs(A[4][2]) * ext[2];
+    const double d0 = A[0][0] * tc[0] + A[0][1] * tc[1] + A[0][2] * tc[2] + A[0][3];
+    const double d2 = A[2][0] * tc[0] + A[2][1] * tc[1] + A[2][2] * tc[2] + A[2][3];
+    const double d4 = A[4][0] * tc[0] + A[4][1] * tc[1] + A[4][2] * tc[2] + A[4][3];
+    const double zmin = d4 - e4, zmax = d4 + e4;
+    if (c.std_frame && zmin > 1e-3 && isfinite(zmax) && isfinite(d0) && isfinite(d2)) {
+      const double xl = fmin((d0 - e0) / zmin, (d0 - e0) / zmax), xh = fmax((d0 + e0) / zmin, (d0 + e0) / zmax);
+      const double yl = fmin((d2 - e2) / zmin, (d2 - e2) / zmax), yh = fmax((d2 + e2) / zmin, (d2 + e2) / zmax);
+      if (xh >= -1.0 && yh >= -1.0 && xl <= dw && yl <= dh) {
+        const int x0 = (int)fmax(floor(xl) - 1.0, 0.0), x1 = (int)fmin(ceil(xh) + 1.0, dw - 1.0);
+        const int y0 = (int)fmax(floor(yl) - 1.0, 0.0), y1 = (int)fmin(ceil(yh) + 1.0, dh - 1.0);
+        const int l0 = (x0 * 2) >> 7, l1 = (x1 * 2) >> 7;   // 128-byte lines within a row (rows are dw * 2 bytes apart; see the prefetch loop)
+        const int rows = y1 - y0 + 1, lines = l1 - l0 + 1;
+        if (rows > 0 && rows < 512 && y0 < 512 && lines > 0 && lines < 1024 && l0 < 16 && lines * rows <= 2048)
+          c.bbox = (uint32_t)y0 | ((uint32_t)rows << 9) | ((uint32_t)l0 << 18) | ((uint32_t)lines << 22);
+      }
+    }
+  }
+}
+
+struct Cull9Params {
+  CullParams p;               // the caller's arrays (msp_cull.cuh)
+  const CullTilePrep* prep;   // one per tile (k_cull_prepare)
+  f32x2 nfdw2, nfdh2;         // (-dw,-dw), (-dh,-dh)
+  f32x2 fdw2;                 // (dw, dw)
+  f32x2 magic2;               // (1.5 * 2^23) x 2
+  f32x2 two23_2, ntwo23_2;    // (2^23) x 2, (-2^23) x 2
+  f32x2 fscale2, c36_2;       // depth scale, 3.6e-7
+  float xclip, yclip;         // dw - 1 + 2^23, dh - 1
+};
+
+// ================================================================================================================
+// main kernel
+// ================================================================================================================
+template <int DT, bool COUNT>
+__global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(const Cull9Params q) {
+  extern __shared__ __align__(128) unsigned char s_raw[];  // CullTilePrep (without pt_slot when !COUNT)
+  __shared__ __align__(16) C9Frame s_c[kC9Frames];
+  __shared__ uint32_t s_cnt[COUNT ? kC9Frames * kC9Slots : 1];  // per (frame, local slot) visible counts
+  __shared__ uint16_t s_dq[kC9Warps][kC9DeferCap];              // (frame in chunk << 8) | (k << 6) | (half << 5) | lane
+  __shared__ __align__(8) uint64_t s_bar;
+  const CullParams& p = q.p;
+  const CullTilePrep& T = *reinterpret_cast<const CullTilePrep*>(s_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * kC9TilePoints;
+  const int cnt = (int)min((int64_t)kC9TilePoints, p.n - base);
+  const int f0 = blockIdx.y * kC9Frames;
+  const int nf = min(kC9Frames, p.F - f0);
+  const CullTilePrep* gprep = q.prep + blockIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  if (COUNT)
+    for (int i = tid; i < kC9Frames * kC9Slots; i += kC9Threads) s_cnt[i] = 0u;
+  __syncthreads();
+  if (tid == 0) {
+    constexpr uint32_t bytes = COUNT ? (uint32_t)sizeof(CullTilePrep) : (uint32_t)offsetof(CullTilePrep, pt_slot);
+    mbar_arrive_expect_tx(&s_bar, bytes);
+    bulk_g2s(s_raw, gprep, bytes, &s_bar);
+  }
+  // per-frame constants while the tile is in flight (the header is read straight from global memory / L2)
+  if (tid < nf) {
+    const float centre[3] = {__ldg(&gprep->centre[0]), __ldg(&gprep->centre[1]), __ldg(&gprep->centre[2])};
+    const float extf[3] = {__ldg(&gprep->ext[0]), __ldg(&gprep->ext[1]), __ldg(&gprep->ext[2])};
+    c9_frame_consts(p.w2c + (int64_t)(f0 + tid) * 16, p.K, p.g, centre, extf, p.depth + (int64_t)(f0 + tid) * p.depth_stride, s_c[tid]);
+  }
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t word0 = (int64_t)blockIdx.x * kC9TileWords;
+  uint32_t okm = 0;  // bit k: the two mask words of this warp's super-group k exist (mask_stride is a multiple of 4)
+#pragma unroll
+  for (int k = 0; k < kC9SgPerWarp; ++k)
+    if (word0 + 2 * MSP_C9_SG(warp, k) < p.mask_stride) okm |= 1u << k;
+  uint32_t* mask0 = p.mask + (int64_t)f0 * p.mask_stride + word0;  // + fi * mask_stride + 2 * sg
+#if MSP_C9_MASK0_REG
+  asm volatile("" : "+l"(mask0));  // kept in a register pair instead of being rebuilt from blockIdx at every store
+#endif
+  // this lane's points of super-group k are at shared address s_lane + kSgStride k (+0 x, +256 y, +512 z); the address is made
+  // opaque so that it stays in a register instead of being re-derived from the thread id at every use
+  uint32_t s_lane = smem_u32(s_raw) + (uint32_t)MSP_C9_SG(warp, 0) * 768u + (uint32_t)lane * 8u;
+  asm volatile("" : "+r"(s_lane));
+  constexpr uint32_t kSgStride = (uint32_t)(MSP_C9_SG(0, 1) - MSP_C9_SG(0, 0)) * 768u;
+  // ---- A: classification, lane = frame.  gmr[r] bit k: super-group k of this warp may be visible in frame 32 r + lane.
+  uint32_t gmr[kC9Rounds];
+#pragma unroll
+  for (int r = 0; r < kC9Rounds; ++r) {
+    const int fi = 32 * r + lane;
+    uint32_t gm = 0u;
+    if (fi < nf) {
+      const C9Frame& c = s_c[fi];
+      const float4 a0l = *reinterpret_cast<const float4*>(&c.a0[0]), a0h = *reinterpret_cast<const float4*>(&c.a0[2]);
+      const float4 a2l = *reinterpret_cast<const float4*>(&c.a2[0]), a2h = *reinterpret_cast<const float4*>(&c.a2[2]);
+      const float4 q1 = *reinterpret_cast<const float4*>(c.q1), q3 = *reinterpret_cast<const float4*>(c.q3);
+      const float nB = -c.B;
+#pragma unroll
+      for (int k = 0; k < kC9SgPerWarp; ++k) {
+        const float4 bc = T.box[MSP_C9_SG(warp, k)][0], bh = T.box[MSP_C9_SG(warp, k)][1];
+        // form value at the box centre + |a| . half size (rounded up) >= -B for all four forms; NaN (empty box, NaN pose) -> false
+        const float v0 = fmaf(a0l.x, bc.x, fmaf(a0l.z, bc.y, fmaf(a0h.x, bc.z, a0h.z)));
+        const float r0 = __fmaf_ru(fabsf(a0l.x), bh.x, __fmaf_ru(fabsf(a0l.z), bh.y, __fmul_ru(fabsf(a0h.x), bh.z)));
+        const float v1 = fmaf(q1.x, bc.x, fmaf(q1.y, bc.y, fmaf(q1.z, bc.z, q1.w)));
+        const float r1 = __fmaf_ru(fabsf(q1.x), bh.x, __fmaf_ru(fabsf(q1.y), bh.y, __fmul_ru(fabsf(q1.z), bh.z)));
+        const float v2 = fmaf(a2l.x, bc.x, fmaf(a2l.z, bc.y, fmaf(a2h.x, bc.z, a2h.z)));
+        const float r2 = __fmaf_ru(fabsf(a2l.x), bh.x, __fmaf_ru(fabsf(a2l.z), bh.y, __fmul_ru(fabsf(a2h.x), bh.z)));
+        const float v3 = fmaf(q3.x, bc.x, fmaf(q3.y, bc.y, fmaf(q3.z, bc.z, q3.w)));
+        const float r3 = __fmaf_ru(fabsf(q3.x), bh.x, __fmaf_ru(fabsf(q3.y), bh.y, __fmul_ru(fabsf(q3.z), bh.z)));
+        const bool cand = (__fadd_ru(v0, r0) >= nB) && (__fadd_ru(v1, r1) >= nB) && (__fadd_ru(v2, r2) >= nB) && (__fadd_ru(v3, r3) >= nB);
+        if (cand) gm |= 1u << k;
+      }
+      // zero words are written here, once, by the frame's lane: all of a frame without candidates (it never reaches the
+      // main loop); the pair loop stores per super-group, so there the non-candidate ones of every frame are written too
+      uint32_t* zrow = mask0 + (int64_t)fi * p.mask_stride;
+#pragma unroll
+      for (int k = 0; k < kC9SgPerWarp; ++k)
+        if ((MSP_C9_LOOP != 2 ? gm == 0u : !((gm >> k) & 1u)) && ((okm >> k) & 1u))
+          *reinterpret_cast<uint2*>(zrow + 2 * MSP_C9_SG(warp, k)) = make_uint2(0u, 0u);
+    }
+    gmr[r] = gm;
+  }
+
+  uint32_t dq = 0;  // warp-uniform fill of s_dq[warp]
+  // one deferred point on this lane: exact re-evaluation in the reference's float64 operation order; a visible point is OR-ed
+  // into its (already stored) mask word and counted.  Callers order the plain mask stores before this with __syncwarp().
+  auto exact_deferred = [&](uint32_t e) {
+    const int fi = (int)(e >> 8), k = (int)((e >> 6) & 3u), sl = (int)(e & 63u);  // sl = half * 32 + lane
+    const int sg = MSP_C9_SG(warp, k);
+    const int idx = sg * 64 + sl;
+    const int64_t f = f0 + fi;
+    const double* w = p.w2c + f * 16;
+    const bool fstd = s_c[fi].std_frame != 0;
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (idx < cnt) PtTraits<DT>::load(p.pts, base + idx, x, y, z);
+    const Proj pr = fstd ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
+    if (idx < cnt && in_image(pr, p.g) && pr.z > 0.0) {
+      const int di = depth_index(pr, p.g);
+      if (depth_test(pr.z, ldg_u16_nc(p.depth + f * p.depth_stride + di), p.g)) {
+        atomicOr(p.mask + f * p.mask_stride + word0 + 2 * sg + (sl >> 5), 1u << (sl & 31));
+        if (COUNT) {
+          const uint32_t s = T.pt_slot[idx];
+          if (s < (uint32_t)(kC9Slots - 1)) atomicAdd(&s_cnt[fi * kC9Slots + s], 1u);
+          else if (s == kC9SlotOverflow) atomicAdd(p.counts + f * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
+        }
+      }
+    }
+  };
+  // run the exact path on the queue's tail, 32 entries at a time, while it holds at least `keep_below` entries
+  auto flush = [&](uint32_t keep_below) {
+    __syncwarp();  // queue entries and the plain mask stores of lane 0 are visible to the whole warp
+    while (dq >= keep_below && dq != 0u) {
+      const uint32_t nb = dq < 32u ? dq : 32u;
+      if (lane < nb) exact_deferred(s_dq[warp][dq - nb + lane]);
+      dq -= nb;
+    }
+    __syncwarp();  // the queue may be refilled
+  };
+
+#if MSP_C9_LOOP == 3
+  // ---- B + C: frames with candidates, ascending.  Within a frame the candidate super-groups are software-pipelined by one:
+  // while the two depth gathers of super-group k are in flight the warp projects the next candidate, and only then compares k;
+  // the last one of the frame is compared at the frame's end (nothing is carried over the loop's back-edge: ptxas then shares
+  // the gather's scoreboard with the loop head's FLO / SHFL and waits there, profiles/r2/k1_tuning.md).
+  // A lane that does not gather (outside the image, or uncertain) reads pixel 0 of the map (always mapped, L1-resident) and
+  // carries z = +inf ("certainly not visible") or z = NaN ("uncertain"): t = z - d is then +inf / NaN for any d, so
+  // `t < -mz` is false and the uncertainty test !(|t| > mz) is false / true as required — the comparison needs no predicates.
+  const float finf = __int_as_float(0x7f800000), qnan = __int_as_float(0x7fc00000);
+  const int my_sg = MSP_C9_SG(warp, lane & 3);  // lanes 0..3 own the two mask words (and the counter slot) of super-group k = lane
+  const bool my_store = (lane < kC9SgPerWarp) && ((okm >> lane) & 1u);
+  uint32_t my_slot = kC9SlotNone;  // COUNT: sg_slot of super-group k = lane (lanes 0..3)
+  if (COUNT && lane < kC9SgPerWarp) my_slot = T.sg_slot[my_sg];
+  uint32_t s_cnt_lane = smem_u32(&s_cnt[0]) + 4u * (my_slot & (uint32_t)(kC9Slots - 1));
+  asm volatile("" : "+r"(s_cnt_lane));
+#pragma unroll 1
+  for (int r = 0; r < kC9Rounds; ++r) {
+    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
+#pragma unroll 1
+    while (fm != 0u) {
+      const int fl = __ffs(fm) - 1;
+      fm &= fm - 1u;
+      const uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
+      const int fi = 32 * r + fl;
+      const uint32_t s_cf = smem_u32(&s_c[fi]);
+#if !MSP_C9_COEF_PER_SG
+      f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
+      lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
+      lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
+      lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
+#endif
+      f32x2 ct1_2, hct0_2, Bz2, BB;
+      lds128(s_cf + 128, ct1_2, hct0_2);
+      lds128(s_cf + 144, Bz2, BB);
+      float Bq, B2q;
+      upk2(BB, Bq, B2q);
+      const float nB = -Bq;
+      const unsigned long long dm = lds64(s_cf + 160);
+      uint32_t* row = mask0 + (int64_t)fi * p.mask_stride + 2 * my_sg;  // lanes 0..3: this frame's two words of super-group k = lane
+      asm volatile("" : "+l"(row));
+      uint32_t wl = 0u, wh = 0u;  // lanes 0..3: those two words
+      int pk = -1;                // pending super-group (its gathers are in flight), -1 = none
+      f32x2 pz = 0ull;
+      uint32_t prl = 0u, prh = 0u;
+      auto finish = [&]() {
+        // depth: d^ = fl(float(raw) * 0.001f); visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^)
+        const f32x2 d = mul2(add2(pk2(__uint_as_float(0x4B000000u | prl), __uint_as_float(0x4B000000u | prh)), q.ntwo23_2), q.fscale2);
+        const f32x2 mz = fma2(q.c36_2, d, Bz2);
+        const f32x2 t = sub2(pz, d);
+        float tl, th, mzl, mzh;
+        upk2(t, tl, th), upk2(mz, mzl, mzh);
+        const bool visl = tl < -mzl, vish = th < -mzh;
+        const bool uncl = !(fabsf(tl) > mzl), unch = !(fabsf(th) > mzh);
+        const uint32_t bvl = __ballot_sync(0xffffffffu, visl), bvh = __ballot_sync(0xffffffffu, vish);
+        const uint32_t bu = __ballot_sync(0xffffffffu, uncl | unch);
+        if (lane == pk) wl = bvl, wh = bvh;
+        if (bu != 0u) {  // rare, warp-uniform: queue the uncertain lanes (lo half first); flushed after this frame's words are stored
+          const uint32_t bul = __ballot_sync(0xffffffffu, uncl), buh = __ballot_sync(0xffffffffu, unch);
+          const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)pk << 6) | (uint32_t)lane;
+          if (uncl) s_dq[warp][dq + __popc(bul & lt)] = (uint16_t)code;
+          dq += __popc(bul);
+          if (unch) s_dq[warp][dq + __popc(buh & lt)] = (uint16_t)(code | 32u);
+          dq += __popc(buh);
+        }
+      };
+#pragma unroll
+      for (int k = 0; k < kC9SgPerWarp; ++k) {
+        if (!((g >> k) & 1u)) continue;  // warp-uniform
+        const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
+        const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
+#if MSP_C9_COEF_PER_SG
+        f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
+        lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
+        lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
+        lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
+#endif
+        const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
+        const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
+        const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
+        const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);  // I0 - dw Z = -Q1 (same rounding as fl(dw Z - I0))
+        const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
+        float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
+        upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
+        // m = min(I0, Q1, I1, Q3); NaN only for empty / non-finite slots: never visible, never queued
+        const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
+        const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
+        const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));  // s = -1/Z (max relative error 2^-23, covered by ct0/ct1)
+        // rint(t) with t = I0 / Z: (-t + 1.5 * 2^23) is an exact integer shift for |t| < 2^22; lanes beyond are never `go`
+        const f32x2 nixm = fma2(I0, s, q.magic2);
+        const f32x2 ix = sub2(q.magic2, nixm);  // = rint(tx), exact
+        const f32x2 fx = fma2(I0, s, ix);       // rint(tx) - tx
+        const f32x2 niym = fma2(I1, s, q.magic2);
+        const f32x2 iy = sub2(q.magic2, niym);
+        const f32x2 fy = fma2(I1, s, iy);
+        const f32x2 thr = fma2(ct1_2, s, hct0_2);  // 1/2 - ct0 - ct1 / Z
+        float fxl, fxh, fyl, fyh, thl, thh;
+        upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
+        // the reference rounds to the same depth pixel, and the point is certainly inside the image in front of the camera
+        const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
+        const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
+        // gather index: di + 2^23 as an exact float, i.e. the bit pattern 0x4B000000 + di (dm is pre-biased by that constant)
+        const f32x2 ixb = add2(ix, q.two23_2);
+        float ixl, ixh, iyl, iyh;
+        upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
+        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
+        float dbl, dbh;
+        upk2(dbits, dbl, dbh);
+        const uint32_t bitl = gol ? __float_as_uint(dbl) : 0x4B000000u, bith = goh ? __float_as_uint(dbh) : 0x4B000000u;
+        const f32x2 zsel = pk2(gol ? Zl : ((ml >= nB) ? qnan : finf), goh ? Zh : ((mh >= nB) ? qnan : finf));
+        if (pk >= 0) finish();  // the previous candidate's gathers have had this whole projection to land
+        prl = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bitl));
+        prh = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bith));
+        pz = zsel;
+        pk = k;
+      }
+      finish();  // g != 0: there is always a pending super-group here
+      // lanes 0..3 store their super-group's two words (zero for a non-candidate super-group of this frame) and count them
+      if (my_store) *reinterpret_cast<uint2*>(row) = make_uint2(wl, wh);
+      if (COUNT) {
+        const bool nz = (wl | wh) != 0u;  // only lanes 0..3 can hold a non-zero word
+        if (nz && my_slot < (uint32_t)(kC9Slots - 1)) red_smem_add(s_cnt_lane + (uint32_t)fi * (4u * kC9Slots), (uint32_t)(__popc(wl) + __popc(wh)));
+        uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
+        // super-groups that straddle an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
+#pragma unroll 1
+        while (mg != 0u) {
+          const int k = __ffs(mg) - 1;
+          mg &= mg - 1u;
+          const uint32_t wvl = __shfl_sync(0xffffffffu, wl, k), wvh = __shfl_sync(0xffffffffu, wh, k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
+            const uint32_t sl = T.pt_slot[idx];
+            const bool bit = (((h ? wvh : wvl) >> lane) & 1u) != 0u;
+            const bool act = bit && sl < (uint32_t)(kC9Slots - 1);
+            const uint32_t am = __ballot_sync(0xffffffffu, act);
+            if (act) {
+              const uint32_t grp = __match_any_sync(am, sl);
+              if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
+            }
+            if (bit && sl == kC9SlotOverflow)
+              atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
+          }
+        }
+      }
+      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
+    }
+  }
+#elif MSP_C9_LOOP == 0
+  // ---- B + C: frames with candidates, ascending; per candidate super-group the packed float32 evaluation of 64 points
+  // lanes 0..3 own the two mask words (and the counter slot) of the warp's super-group k = lane
+  const int my_sg = MSP_C9_SG(warp, lane & 3);
+  const bool my_store = (lane < kC9SgPerWarp) && ((okm >> lane) & 1u);
+  uint32_t my_slot = kC9SlotNone;  // COUNT: sg_slot of super-group k = lane (lanes 0..3)
+  if (COUNT && lane < kC9SgPerWarp) my_slot = T.sg_slot[my_sg];
+  uint32_t s_cnt_lane = smem_u32(&s_cnt[0]) + 4u * (my_slot & (uint32_t)(kC9Slots - 1));
+  asm volatile("" : "+r"(s_cnt_lane));
+#if MSP_C9_PFL2 > 0
+  // L2 prefetch of the depth windows this tile projects into, a few candidate frames ahead of the gathers (the capture of the
+  // un-prefetched loop: 55 % of the stall samples wait for a gather, half of the L2 accesses go on to DRAM).  Warp w takes
+  // rows w, w + 8, ... of the window; one lane per row.
+  auto prefetch_window = [&](int fi) {
+    const uint32_t bb = s_c[fi].bbox;
+    const uint32_t rows = (bb >> 9) & 511u, lines = bb >> 22;
+    if (rows == 0u) return;
+    const char* m = reinterpret_cast<const char*>(p.depth + (int64_t)(f0 + fi) * p.depth_stride) + (size_t)((bb >> 18) & 15u) * 128u;
+    for (uint32_t rr = (uint32_t)warp + 8u * (uint32_t)lane; rr < rows; rr += 256u) {
+      const char* a = m + (size_t)((bb & 511u) + rr) * (size_t)(p.g.depth_w * 2);
+      for (uint32_t l = 0; l < lines; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128u));
+    }
+  };
+#endif
+#pragma unroll 1
+  for (int r = 0; r < kC9Rounds; ++r) {
+    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
+#if MSP_C9_PFL2 > 0
+    {  // start-up: the first MSP_C9_PFL2 candidate frames of the round
+      uint32_t t = fm;
+#pragma unroll 1
+      for (int i = 0; i < MSP_C9_PFL2 && t != 0u; ++i) {
+        prefetch_window(32 * r + __ffs(t) - 1);
+        t &= t - 1u;
+      }
+    }
+#endif
+#pragma unroll 1
+    while (fm != 0u) {
+      const int fl = __ffs(fm) - 1;
+      fm &= fm - 1u;
+#if MSP_C9_PFL2 > 0
+      {  // the candidate frame MSP_C9_PFL2 places after this one
+        uint32_t t = fm;
+#pragma unroll
+        for (int i = 1; i < MSP_C9_PFL2; ++i) t &= t - 1u;
+        if (t != 0u) prefetch_window(32 * r + __ffs(t) - 1);
+      }
+#endif
+      const uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
+      const int fi = 32 * r + fl;
+      const uint32_t s_cf = smem_u32(&s_c[fi]);
+      f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
+      lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
+      lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
+      lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
+      f32x2 ct1_2, hct0_2, Bz2, BB;
+      lds128(s_cf + 128, ct1_2, hct0_2);
+      lds128(s_cf + 144, Bz2, BB);
+      float Bq, B2q;
+      upk2(BB, Bq, B2q);
+      const float nB = -Bq;
+      const unsigned long long dm = lds64(s_cf + 160);
+      uint32_t* row = mask0 + (int64_t)fi * p.mask_stride + 2 * my_sg;  // lanes 0..3: this frame's two words of super-group k = lane
+      asm volatile("" : "+l"(row));
+      uint32_t wl = 0u, wh = 0u;  // lanes 0..3: those two words
+#pragma unroll
+      for (int k = 0; k < kC9SgPerWarp; ++k) {
+        if (!((g >> k) & 1u)) continue;  // warp-uniform
+        const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
+        const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
+        const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
+        const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
+        const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
+        const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);  // I0 - dw Z = -Q1 (same rounding as fl(dw Z - I0))
+        const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
+        float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
+        upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
+        // m = min(I0, Q1, I1, Q3); NaN only for empty / non-finite slots: never visible, never queued
+        const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
+        const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
+        const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));  // s = -1/Z (max relative error 2^-23, covered by ct0/ct1)
+        // rint(t) with t = I0 / Z: (-t + 1.5 * 2^23) is an exact integer shift for |t| < 2^22; lanes beyond are never `go`
+        const f32x2 nixm = fma2(I0, s, q.magic2);
+        const f32x2 ix = sub2(q.magic2, nixm);  // = rint(tx), exact
+        const f32x2 fx = fma2(I0, s, ix);       // rint(tx) - tx
+        const f32x2 niym = fma2(I1, s, q.magic2);
+        const f32x2 iy = sub2(q.magic2, niym);
+        const f32x2 fy = fma2(I1, s, iy);
+        const f32x2 thr = fma2(ct1_2, s, hct0_2);  // 1/2 - ct0 - ct1 / Z
+        float fxl, fxh, fyl, fyh, thl, thh;
+        upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
+        // the reference rounds to the same depth pixel, and the point is certainly inside the image in front of the camera
+        const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
+        const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
+        // gather index: di + 2^23 as an exact float, i.e. the bit pattern 0x4B000000 + di (dm is pre-biased by that constant)
+        const f32x2 ixb = add2(ix, q.two23_2);
+        float ixl, ixh, iyl, iyh;
+        upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
+        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
+        float dbl, dbh;
+        upk2(dbits, dbl, dbh);
+        uint32_t rawl = 0u, rawh = 0u;
+        if (gol) rawl = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * __float_as_uint(dbl)));
+        if (goh) rawh = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * __float_as_uint(dbh)));
+        // depth: d^ = fl(float(raw) * 0.001f); visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^)
+        const f32x2 d = mul2(add2(pk2(__uint_as_float(0x4B000000u | rawl), __uint_as_float(0x4B000000u | rawh)), q.ntwo23_2), q.fscale2);
+        const f32x2 mz = fma2(q.c36_2, d, Bz2);
+        const f32x2 t = sub2(Zp, d);
+        float tl, th, mzl, mzh;
+        upk2(t, tl, th), upk2(mz, mzl, mzh);
+        const bool visl = gol && (tl < -mzl), vish = goh && (th < -mzh);
+        const bool uncl = gol ? (fabsf(tl) <= mzl) : (ml >= nB);
+        const bool unch = goh ? (fabsf(th) <= mzh) : (mh >= nB);
+        const uint32_t bvl = __ballot_sync(0xffffffffu, visl), bvh = __ballot_sync(0xffffffffu, vish);
+        const uint32_t bu = __ballot_sync(0xffffffffu, uncl | unch);
+        if (lane == k) wl = bvl, wh = bvh;
+        if (bu != 0u) {  // rare, warp-uniform: queue the uncertain lanes (lo half first); flushed after this frame's words are stored
+          const uint32_t bul = __ballot_sync(0xffffffffu, uncl), buh = __ballot_sync(0xffffffffu, unch);
+          const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)k << 6) | (uint32_t)lane;
+          if (uncl) s_dq[warp][dq + __popc(bul & lt)] = (uint16_t)code;
+          dq += __popc(bul);
+          if (unch) s_dq[warp][dq + __popc(buh & lt)] = (uint16_t)(code | 32u);
+          dq += __popc(buh);
+        }
+      }
+      // lanes 0..3 store their super-group's two words (zero for a non-candidate super-group of this frame) and count them
+      if (my_store) *reinterpret_cast<uint2*>(row) = make_uint2(wl, wh);
+      if (COUNT) {
+        const bool nz = (wl | wh) != 0u;  // only lanes 0..3 can hold a non-zero word
+        if (nz && my_slot < (uint32_t)(kC9Slots - 1)) red_smem_add(s_cnt_lane + (uint32_t)fi * (4u * kC9Slots), (uint32_t)(__popc(wl) + __popc(wh)));
+        uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
+        // super-groups that straddle an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
+#pragma unroll 1
+        while (mg != 0u) {
+          const int k = __ffs(mg) - 1;
+          mg &= mg - 1u;
+          const uint32_t wvl = __shfl_sync(0xffffffffu, wl, k), wvh = __shfl_sync(0xffffffffu, wh, k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
+            const uint32_t sl = T.pt_slot[idx];
+            const bool bit = (((h ? wvh : wvl) >> lane) & 1u) != 0u;
+            const bool act = bit && sl < (uint32_t)(kC9Slots - 1);
+            const uint32_t am = __ballot_sync(0xffffffffu, act);
+            if (act) {
+              const uint32_t grp = __match_any_sync(am, sl);
+              if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
+            }
+            if (bit && sl == kC9SlotOverflow)
+              atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
+          }
+        }
+      }
+      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
+    }
+  }
+#else
+  // ---- B + C: frames with candidates in ascending order; within a frame the candidate super-groups are taken two at a time:
+  // project A, issue A's two depth gathers, project B, issue B's gathers, then compare A and B.  The gathers of a pair overlap
+  // each other and B's projection (round-2 capture of the one-at-a-time loop: 46 % of all stall samples sat on the first
+  // consumer of a gather; a pipeline that carried the pending gather over the loop's back-edge made ptxas share the gather's
+  // scoreboard with the loop head's FLO and wait there — profiles/r2/k1_tuning.md).
+  // A lane that does not gather (outside the image, or uncertain) reads pixel 0 of the map (always mapped, L1-resident) and
+  // carries z = +inf ("certainly not visible") or z = NaN ("uncertain"): t = z - d is then +inf / NaN for any d, so
+  // `t < -mz` is false and the uncertainty test !(|t| > mz) is false / true as required — stage 2 needs no predicates.
+  const float finf = __int_as_float(0x7f800000), qnan = __int_as_float(0x7fc00000);
+  uint32_t sgslots = 0;  // COUNT: sg_slot of this warp's four super-groups, one byte each
+  if (COUNT) {
+#pragma unroll
+    for (int k = 0; k < kC9SgPerWarp; ++k) sgslots |= (uint32_t)T.sg_slot[MSP_C9_SG(warp, k)] << (8 * k);
+  }
+  const uint32_t s_cnt0 = smem_u32(&s_cnt[0]);
+
+  struct Pending {
+    f32x2 z;             // (z lo, z hi) or +inf / NaN, see above
+    uint32_t rawl, rawh; // the gathered depth values (u16)
+  };
+  // stage 1 of item (frame constants at s_cf, super-group k): packed float32 projection of 64 points, gathers issued
+  auto project = [&](uint32_t s_cf, int k) -> Pending {
+    const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
+    const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
+    f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
+    lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
+    lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
+    lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
+    const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
+    const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
+    const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
+    const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);  // I0 - dw Z = -Q1 (same rounding as fl(dw Z - I0))
+    const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
+    float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
+    upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
+    // m = min(I0, Q1, I1, Q3); NaN only for empty / non-finite slots: never visible, never queued
+    const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
+    const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
+    const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));  // s = -1/Z (max relative error 2^-23, covered by ct0/ct1)
+    // rint(t) with t = I0 / Z: (-t + 1.5 * 2^23) is an exact integer shift for |t| < 2^22; lanes beyond are never `go`
+    const f32x2 nixm = fma2(I0, s, q.magic2);
+    const f32x2 ix = sub2(q.magic2, nixm);  // = rint(tx), exact
+    const f32x2 fx = fma2(I0, s, ix);       // rint(tx) - tx
+    const f32x2 niym = fma2(I1, s, q.magic2);
+    const f32x2 iy = sub2(q.magic2, niym);
+    const f32x2 fy = fma2(I1, s, iy);
+    // the frame's scalars are re-read from shared memory per item: holding them in registers across the pair made the
+    // compiler spill the gather results (and wait for them) right after the loads
+    f32x2 ct1_2, hct0_2;
+    lds128(s_cf + 128, ct1_2, hct0_2);
+    float Bq, B2q;
+    upk2(lds64(s_cf + 152), Bq, B2q);
+    const float nB = -Bq;
+    const unsigned long long dm = lds64(s_cf + 160);
+    const f32x2 thr = fma2(ct1_2, s, hct0_2);  // 1/2 - ct0 - ct1 / Z
+    float fxl, fxh, fyl, fyh, thl, thh;
+    upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
+    // the reference rounds to the same depth pixel, and the point is certainly inside the image in front of the camera
+    const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
+    const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
+    // gather index: di + 2^23 as an exact float, i.e. the bit pattern 0x4B000000 + di (dm is pre-biased by that constant)
+    const f32x2 ixb = add2(ix, q.two23_2);
+    float ixl, ixh, iyl, iyh;
+    upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
+    const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
+    float dbl, dbh;
+    upk2(dbits, dbl, dbh);
+    const uint32_t bitl = gol ? __float_as_uint(dbl) : 0x4B000000u, bith = goh ? __float_as_uint(dbh) : 0x4B000000u;
+    Pending r;
+    r.z = pk2(gol ? Zl : ((ml >= nB) ? qnan : finf), goh ? Zh : ((mh >= nB) ? qnan : finf));
+    r.rawl = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bitl));
+    r.rawh = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bith));
+    return r;
+  };
+  // stage 2: depth comparison, ballots, mask words, counts, queueing of the uncertain lanes
+  auto finish = [&](const Pending& pd, uint32_t s_cf, int fi, int k) {
+    const f32x2 Bz2 = lds64(s_cf + 144);
+    const uint32_t rowoff = (uint32_t)fi * (uint32_t)p.mask_stride;  // < 2^32: checked by the host
+    // depth: d^ = fl(float(raw) * 0.001f); visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^)
+    const f32x2 d = mul2(add2(pk2(__uint_as_float(0x4B000000u | pd.rawl), __uint_as_float(0x4B000000u | pd.rawh)), q.ntwo23_2), q.fscale2);
+    const f32x2 mz = fma2(q.c36_2, d, Bz2);
+    const f32x2 t = sub2(pd.z, d);
+    float tl, th, mzl, mzh;
+    upk2(t, tl, th), upk2(mz, mzl, mzh);
+    const bool visl = tl < -mzl, vish = th < -mzh;
+    const bool uncl = !(fabsf(tl) > mzl), unch = !(fabsf(th) > mzh);
+    const uint32_t bvl = __ballot_sync(0xffffffffu, visl), bvh = __ballot_sync(0xffffffffu, vish);
+    const uint32_t bu = __ballot_sync(0xffffffffu, uncl | unch);
+    if (lane == 0 && ((okm >> k) & 1u)) *reinterpret_cast<uint2*>(mask0 + (rowoff + 2u * (uint32_t)MSP_C9_SG(warp, k))) = make_uint2(bvl, bvh);
+    if (bu != 0u) {  // rare, warp-uniform: queue the uncertain lanes (lo half first)
+      const uint32_t bul = __ballot_sync(0xffffffffu, uncl), buh = __ballot_sync(0xffffffffu, unch);
+      const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)k << 6) | (uint32_t)lane;
+      if (uncl) s_dq[warp][dq + __popc(bul & lt)] = (uint16_t)code;
+      dq += __popc(bul);
+      if (unch) s_dq[warp][dq + __popc(buh & lt)] = (uint16_t)(code | 32u);
+      dq += __popc(buh);
+    }
+    if (COUNT && (bvl | bvh) != 0u) {
+      const uint32_t slot = (sgslots >> (8 * k)) & 0xffu;  // warp-uniform
+      if (slot < (uint32_t)(kC9Slots - 1)) {
+        if (lane == 0) red_smem_add(s_cnt0 + 4u * ((uint32_t)fi * kC9Slots + slot), (uint32_t)(__popc(bvl) + __popc(bvh)));
+      } else if (slot == kC9SlotMixed) {
+        // the super-group straddles an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
+          const uint32_t sl = T.pt_slot[idx];
+          const bool bit = (((h ? bvh : bvl) >> lane) & 1u) != 0u;
+          const bool act = bit && sl < (uint32_t)(kC9Slots - 1);
+          const uint32_t am = __ballot_sync(0xffffffffu, act);
+          if (act) {
+            const uint32_t grp = __match_any_sync(am, sl);
+            if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
+          }
+          if (bit && sl == kC9SlotOverflow)
+            atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
+        }
+      }
+    }
+  };
+
+#pragma unroll 1
+  for (int r = 0; r < kC9Rounds; ++r) {
+    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
+#pragma unroll 1
+    while (fm != 0u) {
+      const int fl = __ffs(fm) - 1;
+      fm &= fm - 1u;
+      uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
+      const int fi = 32 * r + fl;
+      const uint32_t s_cf = smem_u32(&s_c[fi]);
+#pragma unroll 1
+      while (g != 0u) {
+        const int kA = __ffs(g) - 1;
+        g &= g - 1u;
+        const int kB = __ffs(g) - 1;  // -1: no second candidate
+        g &= g - 1u;                  // 0 & anything = 0
+        const Pending A = project(s_cf, kA);
+        if (kB >= 0) {  // warp-uniform
+          const Pending Bp = project(s_cf, kB);
+          finish(A, s_cf, fi, kA);
+          finish(Bp, s_cf, fi, kB);
+        } else {
+          finish(A, s_cf, fi, kA);
+        }
+      }
+      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
+    }
+  }
+#endif
+  if (dq != 0u) flush(1u);
+  if (COUNT) {
+    __syncthreads();
+    for (int i = tid; i < nf * kC9Slots; i += kC9Threads) {
+      const uint32_t v = s_cnt[i];
+      const uint32_t idv = T.slot_id[i % kC9Slots];
+      if (v != 0u && idv != 0u) atomicAdd(p.counts + (int64_t)(f0 + i / kC9Slots) * p.n_objects + (int)idv - 1, v);
+    }
+  }
+}
+
+}  // namespace msp

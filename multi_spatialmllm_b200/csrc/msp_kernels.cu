@@ -10,6 +10,7 @@
 #include "msp.h"
 #include "msp_device.cuh"
 #include "msp_cull.cuh"
+#include "msp_cull9.cuh"
 #include "msp_tables.cuh"
 
 using namespace msp;
@@ -758,8 +759,78 @@ static bool cull_enabled() {
   return !(e != nullptr && e[0] == '1');
 }
 
+// MSP_CULL_V9=0 selects the round-1 kernel (msp_cull.cuh) for the visibility fast path (A/B switch for tests and profiling).
+static bool cull9_enabled() {
+  const char* e = getenv("MSP_CULL_V9");
+  return !(e != nullptr && e[0] == '0');
+}
+
+// K1 second generation (msp_cull9.cuh): prepare pass into a stream-ordered workspace, then the main kernel.
+static int launch_cull9(const FrameLoopParams& p, int dt, cudaStream_t s) {
+  const unsigned tiles = (unsigned)((p.n + kC9TilePoints - 1) / kC9TilePoints);
+  const dim3 grid(tiles, (unsigned)((p.F + kC9Frames - 1) / kC9Frames));
+  REQUIRE(grid.y <= 65535u, "too many frames in one call");
+  CullTilePrep* prep = nullptr;
+  {
+    // keep the workspace in the device's default memory pool between calls (the default threshold of 0 hands it back to
+    // the driver at every synchronisation, and the next call pays a real allocation)
+    static thread_local int pool_ready_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pool_ready_dev != dev) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready_dev = dev;
+    }
+  }
+  if (cudaMallocAsync(reinterpret_cast<void**>(&prep), sizeof(CullTilePrep) * (size_t)tiles, s) != cudaSuccess)
+    return check_launch("msp_project_visibility(workspace)");
+  const bool count = p.counts != nullptr;
+  Cull9Params q{};
+  CullParams& c = q.p;
+  c.pts = p.pts, c.n = p.n, c.w2c = p.w2c, c.F = p.F, c.depth = p.depth, c.zbuf = nullptr;
+  c.depth_stride = p.depth_stride, c.mask = p.mask, c.mask_stride = p.mask_stride, c.K = p.K, c.g = p.g;
+  c.stats = g_cull_stats;
+  c.inst = p.inst, c.counts = p.counts, c.n_objects = p.n_objects;
+  q.prep = prep;
+  const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h, fscale = (float)p.g.depth_scale;
+  auto dup = [](float v) {
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    return (unsigned long long)b | ((unsigned long long)b << 32);
+  };
+  q.nfdw2 = dup(-fdw), q.nfdh2 = dup(-fdh), q.fdw2 = dup(fdw);
+  q.magic2 = dup(12582912.0f), q.two23_2 = dup(8388608.0f), q.ntwo23_2 = dup(-8388608.0f);
+  q.fscale2 = dup(fscale), q.c36_2 = dup(3.6e-7f);
+  q.xclip = (fdw - 1.0f) + 8388608.0f, q.yclip = fdh - 1.0f;
+  int rc = MSP_OK;
+#define MSP_C9_LAUNCH(DT, CNT)                                                                                      \
+  {                                                                                                                 \
+    constexpr int smem = CNT ? (int)sizeof(CullTilePrep) : (int)offsetof(CullTilePrep, pt_slot);                    \
+    k_cull_prepare<DT><<<tiles, kC9Threads, 0, s>>>(p.pts, p.n, count ? p.inst : nullptr, p.n_objects, prep);       \
+    k_frame_cull9<DT, CNT><<<grid, kC9Threads, smem, s>>>(q);                                                       \
+  }
+#define MSP_C9(DT)                        \
+  if (count) MSP_C9_LAUNCH(DT, true)      \
+  else MSP_C9_LAUNCH(DT, false)
+  switch (dt) {
+    case 0: MSP_C9(0) break;
+    case 1: MSP_C9(1) break;
+    default: MSP_C9(2) break;
+  }
+#undef MSP_C9
+#undef MSP_C9_LAUNCH
+  rc = check_launch("k_frame_cull9");
+  if (cudaFreeAsync(prep, s) != cudaSuccess && rc == MSP_OK) rc = check_launch("msp_project_visibility(workspace free)");
+  return rc;
+}
+
 template <int MODE>
 static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool mat, cudaStream_t s) {
+  if (MODE == MODE_VIS && kstd && !mat && cull_enabled() && cull9_enabled()) return launch_cull9(p, dt, s);
   if (kstd && !mat && cull_enabled()) {
     // fast path: float32 conservative cull + exact float64 on compacted survivors (msp_cull.cuh)
     const dim3 grid((unsigned)((p.n + kCullTilePoints - 1) / kCullTilePoints),
@@ -844,7 +915,9 @@ extern "C" int msp_project_visibility_objects(const void* pts, int64_t n, int32_
   REQUIRE(n_objects <= 8191, "n_objects must be <= 8191");
   if (F == 0) return MSP_OK;
   REQUIRE(n_objects == 0 || (instance_ids && counts), "msp_project_visibility_objects: NULL instance_ids / counts");
-  const bool fused = n_objects > 0 && n_objects <= kCullMaxObjects && n > 0 && K16 != nullptr && k_is_std(K16) && cull_enabled();
+  // the second-generation kernel counts any number of objects in the same pass (per-tile local id table); the round-1
+  // kernel (MSP_CULL_V9=0) fuses up to kCullMaxObjects and otherwise needs the second launch below
+  const bool fused = n_objects > 0 && (cull9_enabled() || n_objects <= kCullMaxObjects) && n > 0 && K16 != nullptr && k_is_std(K16) && cull_enabled();
   if (!fused) {  // same result in two launches
     if (int rc = msp_project_visibility(pts, n, pts_dtype, K16, w2c, F, depth, host_cam, mask_bits, mask_stride_words,
                                         nullptr, nullptr, stream)) return rc;

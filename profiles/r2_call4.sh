@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out
+rm -f gpurun_out/r2_call4.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_v10.log 2>&1
+echo pytest_v10 rc=$? >> gpurun_out/r2_call4.txt
+VC_FRAMES=2000 MSP_CULL_V9=0 python profiles/variant_check.py 2>/dev/null | tail -1 >> gpurun_out/r2_call4.txt
+for v in v10 v10m0 v10f32 v10ns v10mb3; do VC_FRAMES=2000 MSP_LIB=$PWD/build/variants/$v.so python profiles/variant_check.py 2>/dev/null | tail -1 >> gpurun_out/r2_call4.txt; done
+for v in v10 v10f32; do MSP_LIB=$PWD/build/variants/$v.so python bench.py --scenes 12 --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.readline()); print('$v', 'pairs/s=%.0f' % d['value'], 'k1_ms=%.4f' % d['roofline']['avg_launch_ms'])" >> gpurun_out/r2_call4.txt; done
+VC_FRAMES=2000 ncu --set full --clock-control none --import-source on -k regex:k_frame_cull9 -s 2 -c 1 -o gpurun_out/prof_v10a python profiles/variant_check.py > gpurun_out/prof_v10a.log 2>&1
+cat gpurun_out/r2_call4.txt; tail -5 gpurun_out/r2_pytest_v10.log

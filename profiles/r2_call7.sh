@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/r2_call7.txt
+./build/ubench_prefetch > gpurun_out/ubench_prefetch.txt 2>&1
+for v in v12pf0 v12 v12pf2 v12pf6 v12f32; do VC_FRAMES=2000 MSP_LIB=$PWD/build/variants/$v.so python profiles/variant_check.py 2>/dev/null | tail -1 >> gpurun_out/r2_call7.txt; done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_v12.log 2>&1
+echo pytest_v12 rc=$? >> gpurun_out/r2_call7.txt
+VC_FRAMES=2000 ncu --set full --clock-control none --import-source on -k regex:k_frame_cull9 -s 2 -c 1 -o gpurun_out/prof_v12 python profiles/variant_check.py > gpurun_out/prof_v12.log 2>&1
+cat gpurun_out/r2_call7.txt gpurun_out/ubench_prefetch.txt; tail -3 gpurun_out/r2_pytest_v12.log
