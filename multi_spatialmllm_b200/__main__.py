@@ -9,9 +9,9 @@ import sys
 
 COMMANDS = {
     # reference script (without .py)                      -> (module, callable, leading argv, reference path)
-    "batch_load_scannet_data": ("ingest", "main", [], "spatial_engine/utils/scannet_utils/batch_load_scannet_data.py"),
-    "extract_posed_images": ("ingest", "main", [], "spatial_engine/utils/scannet_utils/extract_posed_images.py"),
-    "update_info_file_with_images": ("ingest", "main", [], "spatial_engine/utils/scannet_utils/update_info_file_with_images.py"),
+    "batch_load_scannet_data": ("ingest", "load_main", [], "spatial_engine/utils/scannet_utils/batch_load_scannet_data.py"),
+    "extract_posed_images": ("ingest", "extract_main", [], "spatial_engine/utils/scannet_utils/extract_posed_images.py"),
+    "update_info_file_with_images": ("ingest", "update_info_main", [], "spatial_engine/utils/scannet_utils/update_info_file_with_images.py"),
     "make_visibility_info": ("tables", "main", ["visibility"], "spatial_engine/utils/scannet_utils/make_visibility_info.py"),
     "calculate_frames_relations": ("tables", "main", ["relations"], "spatial_engine/camera_movement/calculate_frames_relations.py"),
     "camera_movement_engine_train_val": ("pair_engines", "main", ["camera_movement"],

@@ -40,6 +40,19 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device(fn):
+    """Run a method with ``self.device`` as the CURRENT CUDA device: libmsp launches on the current device and on the
+    stream handed to it, so a scene that lives on cuda:1 must not be driven while cuda:0 is current (multi-GPU processes,
+    torchrun ranks that did not call ``torch.cuda.set_device``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 def _ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -66,6 +79,8 @@ class DeviceScene:
         selecting the k-th common point by its original index (sel_mode 0) is not available on a reordered scene."""
         _require_cuda()
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         pts = points
         if not isinstance(pts, torch.Tensor):
             pts = torch.from_numpy(np.ascontiguousarray(pts))
@@ -113,6 +128,7 @@ class DeviceScene:
             self.set_depth(depth)
 
     # ---- poses ---------------------------------------------------------------------------------
+    @_on_device
     def set_poses(self, c2w, axis_align=None):
         c2w_d = _to_device(np.asarray(c2w, dtype=np.float64).reshape(-1, 16) if not isinstance(c2w, torch.Tensor) else c2w.reshape(-1, 16),
                            torch.float64, self.device)
@@ -127,18 +143,21 @@ class DeviceScene:
                                    _ptr(self.valid), _stream()), "msp_pose_prepare")
         self.mask = None
 
+    @_on_device
     def set_depth(self, depth):
         d = depth if isinstance(depth, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(depth))
         assert d.dtype == torch.uint16 and tuple(d.shape) == (self.F, *self.depth_hw), (d.dtype, d.shape)
         self.depth = d.to(self.device, non_blocking=True).contiguous()
 
     # ---- z-buffer (not in the reference) -------------------------------------------------------
+    @_on_device
     def render_zbuffer(self) -> torch.Tensor:
         zb = torch.empty((self.F, *self.depth_hw), dtype=torch.float32, device=self.device)
         check(lib.msp_zbuffer_render(_ptr(self.pts), self.n, self.pts_dtype, self.K_host.ctypes.data, _ptr(self.w2c),
                                      self.F, C.byref(self.cam), _ptr(zb), _stream()), "msp_zbuffer_render")
         return zb
 
+    @_on_device
     def render_depth(self, margin_mm: int = 1, chunk: int = 256) -> torch.Tensor:
         """Synthetic sensor depth for the scene's own frames (chunked so the fp32 buffer stays small)."""
         out = torch.empty((self.F, *self.depth_hw), dtype=torch.uint16, device=self.device)
@@ -155,6 +174,7 @@ class DeviceScene:
         return out
 
     # ---- K1 ------------------------------------------------------------------------------------
+    @_on_device
     def project_visibility(self, materialize: bool = False):
         assert self.depth is not None, "no depth maps: call set_depth() or render_depth() first"
         if self.mask is None:
@@ -168,6 +188,7 @@ class DeviceScene:
                                          _ptr(xy), _ptr(z), _stream()), "msp_project_visibility")
         return (self.mask, xy, z) if materialize else self.mask
 
+    @_on_device
     def project_visibility_objects(self):
         """Masks and per-(frame, object) visible counts in one pass (msp_project_visibility_objects)."""
         assert self.depth is not None and self.instance_ids is not None and self.num_objects > 0
@@ -189,6 +210,7 @@ class DeviceScene:
         return bits
 
     # ---- pair stage ----------------------------------------------------------------------------
+    @_on_device
     def pair_overlap(self, pairs):
         pairs_d = _to_device(pairs if isinstance(pairs, torch.Tensor) else np.asarray(pairs, dtype=np.int32).reshape(-1, 2),
                              torch.int32, self.device)
@@ -200,6 +222,7 @@ class DeviceScene:
                                    _ptr(ov), _stream()), "msp_pair_overlap")
         return inter, uni, ov
 
+    @_on_device
     def pair_annotate(self, pairs, sel, sel_mode: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
         pairs_d = _to_device(pairs if isinstance(pairs, torch.Tensor) else np.asarray(pairs, dtype=np.int32).reshape(-1, 2),
                              torch.int32, self.device)
@@ -223,6 +246,7 @@ class DeviceScene:
     def records_to_numpy(rec: torch.Tensor) -> np.ndarray:
         return rec.cpu().numpy().view(PAIR_RECORD_DTYPE).reshape(-1)
 
+    @_on_device
     def annotate_points(self, point_ids, frame_ids, use_depth: bool = True):
         pid = _to_device(np.asarray(point_ids, dtype=np.int32), torch.int32, self.device)
         if self.inv_perm is not None:
@@ -240,6 +264,7 @@ class DeviceScene:
               "msp_annotate_points")
         return {"uvz": uvz, "permille": pm, "depth_mm": dmm, "pix": pix, "visible": vis}
 
+    @_on_device
     def object_counts(self) -> torch.Tensor:
         assert self.instance_ids is not None and self.num_objects > 0
         counts = torch.empty((self.F, self.num_objects), dtype=torch.int32, device=self.device)
@@ -248,6 +273,7 @@ class DeviceScene:
         return counts
 
 
+    @_on_device
     def object_extents(self) -> torch.Tensor:
         """(F, n_objects, 6) float64: min xyz / max xyz of each object's visible points per frame (SOCF:57-65)."""
         assert self.instance_ids is not None and self.num_objects > 0 and self.mask is not None
@@ -315,6 +341,7 @@ class DeviceVideo:
         self.image_hw = (int(image_hw[0]), int(image_hw[1]))
         self.world = self.uvn = self.permille = self.valid = None
 
+    @_on_device
     def project(self):
         """World transform + pinhole projection of every (frame, track) (OM-coord:446-451, 293-315)."""
         T, N = self.T, self.N
@@ -327,6 +354,7 @@ class DeviceVideo:
                                     _ptr(self.valid), _stream()), "msp_track_project")
         return self
 
+    @_on_device
     def pair_displacement(self, triples):
         """(M,3) int32 (frame1, frame2, track) -> (M,5) float64: dist, d_cam1 xyz, camera baseline (OM-coord:329-356)."""
         if self.world is None:
@@ -337,6 +365,7 @@ class DeviceVideo:
                                               int(tri.shape[0]), _ptr(out), _stream()), "msp_track_pair_displacement")
         return out
 
+    @_on_device
     def rigid_body_groups(self, threshold: float = 0.1, smoothing_factor: float = 0.01, min_size: int = 5):
         """rigid_body_segmentation + filter_large_groups (OM-coord:49-105): the O(T N^2) accumulation on the GPU,
         average-linkage clustering of the N x N result on the host (scipy, like the reference)."""

@@ -428,18 +428,57 @@ def main(argv=None):
     ap.add_argument("--info_skip", type=int, default=5, help="keep every n-th exported image in the info file (UIF)")
     ap.add_argument("--max_num_point", default=None)
     ap.add_argument("--nproc", type=int, default=1)
+    ap.add_argument("--steps", default="load,extract,update",
+                    help="comma-separated stages: load (batch_load_scannet_data: per-scene npy files + info pkl), extract "
+                         "(extract_posed_images: .sens -> posed images), update (update_info_file_with_images: info pkl + image "
+                         "lists).  The reference runs them as three scripts; each stage only reads what the previous one wrote")
+    ap.add_argument("--info_pkl", default=None, help="info pkl to read when the load stage is skipped "
+                                                     "(default: <output_folder>/../scenes_*_info.pkl written by it)")
     a = ap.parse_args(argv)
-    pkl = batch_export(a.max_num_point, a.output_folder, a.scan_names_file, a.label_map_file, a.scannet_dir,
-                       num_workers=a.nproc)
-    with open(pkl, "rb") as f:
-        infos = pickle.load(f)
-    for scan in infos:
-        extract_posed_images(os.path.join(a.scannet_dir, scan, f"{scan}.sens"), os.path.join(a.posed_images, scan), a.frame_skip)
-    update_info_with_images(infos, a.posed_images, a.info_skip)
-    out = pkl.replace(".pkl", f"_i_D{a.info_skip}.pkl")
-    with open(out, "wb") as f:
-        pickle.dump(infos, f)
-    print(f"wrote {out}")
+    steps = [t.strip() for t in a.steps.split(",") if t.strip()]
+    bad = sorted(set(steps) - {"load", "extract", "update"})
+    if bad:
+        ap.error(f"unknown stage(s) {bad}")
+    pkl = a.info_pkl
+    if "load" in steps:
+        pkl = batch_export(a.max_num_point, a.output_folder, a.scan_names_file, a.label_map_file, a.scannet_dir,
+                           num_workers=a.nproc)
+    infos = None
+    if "update" in steps or ("extract" in steps and pkl and os.path.exists(pkl)):
+        if not pkl or not os.path.exists(pkl):
+            ap.error("the update stage needs the info pkl of the load stage: pass --info_pkl or include 'load' in --steps")
+        with open(pkl, "rb") as f:
+            infos = pickle.load(f)
+    if "extract" in steps:
+        if infos is not None:
+            scans = list(infos)
+        else:
+            with open(a.scan_names_file) as f:
+                scans = [ln.strip() for ln in f if ln.strip()]
+        for scan in scans:
+            extract_posed_images(os.path.join(a.scannet_dir, scan, f"{scan}.sens"), os.path.join(a.posed_images, scan), a.frame_skip)
+    if "update" in steps:
+        update_info_with_images(infos, a.posed_images, a.info_skip)
+        out = pkl.replace(".pkl", f"_i_D{a.info_skip}.pkl")
+        with open(out, "wb") as f:
+            pickle.dump(infos, f)
+        print(f"wrote {out}")
+    return 0
+
+
+def load_main(argv=None):
+    """``batch_load_scannet_data.py`` alone."""
+    return main(list(argv or []) + ["--steps", "load"])
+
+
+def extract_main(argv=None):
+    """``extract_posed_images.py`` alone (does not touch the npy files or the info pkl)."""
+    return main(list(argv or []) + ["--steps", "extract"])
+
+
+def update_info_main(argv=None):
+    """``update_info_file_with_images.py`` alone (needs ``--info_pkl``)."""
+    return main(list(argv or []) + ["--steps", "update"])
 
 
 if __name__ == "__main__":

@@ -94,11 +94,13 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("gloo")                      # host-side gather only; nothing crosses NVLink
     dev = f"cuda:{local}"
+    if torch.cuda.is_available():                            # (DeviceScene raises without CUDA: no CPU fallback)
+        torch.cuda.set_device(local)                         # libmsp launches on the CURRENT device
     handler = None
     if args.info:
         from .handler.info_handler import SceneInfoHandler
         handler = SceneInfoHandler(args.info, args.posed_images_root, args.instance_data_root)
-        costs = {sid: shard.scene_cost(len(handler.get_scene_points_align(sid)), handler.get_num_posed_images(sid))
+        costs = {sid: shard.scene_cost(tables._scene_point_count(handler, sid), handler.get_num_posed_images(sid))
                  for sid in handler.get_all_scene_ids()}
     else:
         costs = {f"scene{i:04d}_00": shard.scene_cost(args.points, args.frames) for i in range(args.synthetic)}

@@ -67,3 +67,19 @@ def merge_jsonl_parts(part_files, output_file: str) -> int:
                     out.write(ln)
                     n += 1
     return n
+
+
+def merge_text_parts(part_files, output_file: str) -> int:
+    """Append the per-rank text parts (e.g. warning files of ranks > 0) to rank 0's file, in rank order; missing parts
+    are skipped and merged parts removed.  Returns the number of lines appended."""
+    n = 0
+    with open(output_file, "a") as out:
+        for p in part_files:
+            if not os.path.exists(p):
+                continue
+            with open(p) as f:
+                for ln in f:
+                    out.write(ln)
+                    n += 1
+            os.remove(p)
+    return n

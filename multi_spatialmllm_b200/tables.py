@@ -397,6 +397,18 @@ def merge_parquet_parts(part_files, output_file: str, scene_order, scene_of=None
     return rows
 
 
+def _scene_point_count(handler, scene_id) -> int:
+    """Number of points of a scene for the cost model WITHOUT loading the array: the .npy header (memory-mapped) when
+    the handler exposes the file, otherwise the array itself."""
+    try:
+        path = os.path.join(handler.instance_data_root, scene_id, "aligned_points.npy")
+        if not os.path.exists(path):
+            path = os.path.join(handler.instance_data_root, f"{scene_id}_aligned_points.npy")
+        return int(np.load(path, mmap_mode="r").shape[0])
+    except Exception:
+        return len(handler.get_scene_points_align(scene_id))
+
+
 def main(argv=None):
     """``python -m multi_spatialmllm_b200.tables {visibility,relations,object_visibility}`` = the ``main()`` of
     make_visibility_info.py, calculate_frames_relations.py and compute_object_visibility.py (val split, then train, the
@@ -417,6 +429,9 @@ def main(argv=None):
     a = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    import torch
+    if torch.cuda.is_available():                            # (the scene workers raise without CUDA: no CPU fallback)
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))   # libmsp launches on the CURRENT device
     if world > 1:
         import torch.distributed as dist
         if not dist.is_initialized():
@@ -438,7 +453,7 @@ def main(argv=None):
         if world == 1:
             results[split] = run(h, out, device=device, warning_file=warn)
             continue
-        costs = {s: shard.scene_cost(len(h.get_scene_points_align(s)), h.get_num_posed_images(s)) for s in scene_ids}
+        costs = {s: shard.scene_cost(_scene_point_count(h, s), h.get_num_posed_images(s)) for s in scene_ids}
         mine = set(shard.my_shard(costs, rank, world))
         part = shard.part_path(out, rank)
         res = run(h, part, scene_ids=[s for s in scene_ids if s in mine], device=device, warning_file=warn)
@@ -458,6 +473,8 @@ def main(argv=None):
                 if a.table == "relations":
                     nz = [p.replace(".parquet", "_nonzero.parquet") for p in parts]
                     res["rows_nonzero"] = merge_parquet_parts(nz, out.replace(".parquet", "_nonzero.parquet"), scene_ids)
+        if rank == 0:                                        # the reference writes ONE warning file per split
+            shard.merge_text_parts([shard.part_path(warn, r) for r in range(1, world)], warn)
         results[split] = res
         import torch.distributed as dist
         dist.barrier()

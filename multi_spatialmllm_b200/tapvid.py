@@ -79,13 +79,16 @@ def all_pair_distances(vid: DeviceVideo, track_ids, visible_frames):
 
 
 def sample_video_pairs(vid: DeviceVideo, visibility, groups, npoints_per_group=5, npairs_per_bin=1e8, augment=True,
-                       augment_ratio=1.0, object_thr=OBJECT_NOT_MOVING_THRESHOLD, rnd=random):
+                       augment_ratio=1.0, object_thr=OBJECT_NOT_MOVING_THRESHOLD, rnd=random, future_frame_windows=None):
     """OM-coord:468-567.  ``groups`` is shuffled in place like the reference's; ``rnd`` is the ``random`` module or a
     ``random.Random``.  Returns [{"point_index", "frame1", "frame2"}, ...] in the reference's order.
 
     Kept quirks: ``npairs_per_bin`` is overwritten by each track's middle-bin count and carries over to the following
-    tracks (OM-coord:535-538); the ``future_frame_windows`` test compares a distance with a frame index and never fires
-    (OM-coord:505-508)."""
+    tracks (OM-coord:535-538); the ``future_frame_windows`` test unpacks (dist, frame1, frame2) as ``frame1, frame2 =
+    disp[0], disp[1]`` and therefore compares the FIRST FRAME INDEX with ``dist + window`` (OM-coord:505-508,
+    OM-dot:550-552).  With the default window of 1e8 it never fires; the dot engine on ``drivetrack`` sets 5
+    (OM-dot:303) and then drops every pair whose first frame index exceeds ``dist + 5`` — replicated when
+    ``future_frame_windows`` is given."""
     visibility = np.asarray(visibility)
     sample_pairs = []
     for group in groups:
@@ -96,6 +99,11 @@ def sample_video_pairs(vid: DeviceVideo, visibility, groups, npoints_per_group=5
         dists = all_pair_distances(vid, [selected[k] for k in keep], [vis[k] for k in keep])
         for k, (d, f1, f2) in zip(keep, dists):
             point_idx = selected[k]
+            if future_frame_windows is not None:
+                ok = ~(f1 > d + future_frame_windows)                    # the reference's mis-unpacked window test
+                d, f1, f2 = d[ok], f1[ok], f2[ok]
+                if len(d) == 0:
+                    continue
             static = d < object_thr
             chosen = []
             if static.any():
@@ -168,7 +176,7 @@ def render_dot_images(video, video_id: str, samples, marks, plan, img_output_dir
 def generate_video_samples(video, video_id: str, question_type="tapvid3d_total_distance", npoints_per_group=5,
                            npairs_per_bin=1e8, img_output_dir=None, image_hw=None, augment=True, augment_ratio=1.0,
                            templates=None, rnd=random, device="cuda:0", dot=False, object_thr=OBJECT_NOT_MOVING_THRESHOLD,
-                           camera_thr=CAMERA_NOT_MOVING_THRESHOLD):
+                           camera_thr=CAMERA_NOT_MOVING_THRESHOLD, future_frame_windows=None):
     """generate_qa_training_single_scene for one video (a dict as returned by ``load_video``): OM-coord:406-575, or with
     ``dot=True`` single_object_movement_engine_dot.py:448-616 (annotated first image, ids ending in ``_ann``; the
     annotated JPEGs go to ``img_output_dir``).  Drivetrack's looser thresholds (OM-dot:301-302) are the two ``*_thr``."""
@@ -183,7 +191,7 @@ def generate_video_samples(video, video_id: str, question_type="tapvid3d_total_d
     vid.project()
     groups, _ = vid.rigid_body_groups()                               # OM-coord:454-455 (threshold 0.1, groups > 5 points)
     pairs = sample_video_pairs(vid, video["visibility"], groups, npoints_per_group, npairs_per_bin, augment, augment_ratio,
-                               object_thr=object_thr, rnd=rnd)
+                               object_thr=object_thr, rnd=rnd, future_frame_windows=future_frame_windows)
     triples = [(int(p["frame1"]), int(p["frame2"]), int(p["point_index"])) for p in pairs]
     if not dot:
         return streams.object_movement_samples(vid, video_id, triples, question_type, object_thr, camera_thr,
@@ -226,6 +234,7 @@ class TwoFrameVideoQAEngine:
         loose = self.dot and sub_dataset == "drivetrack"                         # OM-dot:301-303
         self.object_not_moving_threshold = 0.1 if loose else OBJECT_NOT_MOVING_THRESHOLD
         self.camera_not_moving_threshold = 0.1 if loose else CAMERA_NOT_MOVING_THRESHOLD
+        self.future_frame_windows = 5 if loose else None                         # OM-dot:303 (1e8 elsewhere: never fires)
 
     def project_point(self, point_3d, intrinsics, image_height, image_width, id=""):
         """OM-coord:293-315 through msp_track_project (float64 arithmetic on a float32 track position, which is what the
@@ -253,7 +262,7 @@ class TwoFrameVideoQAEngine:
         return generate_video_samples(load_video(input_file), video_id, self.question_type, a["npoints_per_group"],
                                       a["npairs_per_bin"], a["img_output_dir"] or None, None, a["augment"], a["augment_ratio"],
                                       self.templates, random, self.device, self.dot, self.object_not_moving_threshold,
-                                      self.camera_not_moving_threshold)
+                                      self.camera_not_moving_threshold, self.future_frame_windows)
 
     def _all_videos(self, scene_id_list, source_data_root, npoints_per_group, npairs_per_bin, img_output_dir, augment, augment_ratio):
         data = []

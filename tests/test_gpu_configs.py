@@ -134,3 +134,28 @@ def test_empty_and_ragged_inputs():
     assert not sc2.mask_bool().any()
     rec = sc2.records_to_numpy(sc2.pair_annotate(np.array([[0, 1]], np.int32), np.zeros(1, np.uint32), 0))
     assert rec["uni"][0] == 0 and np.isnan(rec["overlap"][0]) and rec["point_id"][0] == -1
+
+
+@pytest.mark.gpu
+def test_scene_on_second_device_while_first_is_current():
+    """A DeviceScene on cuda:1 driven while cuda:0 is the current device (ADVICE r1: libmsp launches on the current device;
+    the per-device shared-memory attribute).  Needs two GPUs; skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=77, n_points=30_000, n_frames=9, n_objects=5)
+    out = []
+    torch.cuda.set_device(0)
+    for dev in ("cuda:0", "cuda:1"):
+        sc = DeviceScene(s.points.astype(np.float64), s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids,
+                         num_objects=s.num_objects, device=dev)
+        sc.render_depth(1)
+        mask, counts = sc.project_visibility_objects()
+        assert mask.device == torch.device(dev)
+        out.append((sc.mask_bool(), counts.cpu().numpy()))
+    assert torch.cuda.current_device() == 0
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    assert out[0][0].sum() > 0

@@ -160,13 +160,18 @@ def test_object_counts(golden_scannet):
 
 
 def test_fused_object_counts_mixed_groups_and_fallback():
-    """Instance ids that change inside 32-point groups, ids above n_objects, and the >63-object fallback."""
+    """Instance ids that change inside 32-point groups, ids above n_objects, more than 63 / 255 objects (fused for any count)."""
     from multi_spatialmllm_b200 import synth
     from multi_spatialmllm_b200.engine import DeviceScene
     s = synth.make_scene(seed=21, n_points=70_003, n_frames=67, n_objects=9, shuffle_points=False)
     rng = np.random.default_rng(5)
+    # ScanNet-like: 255 / 2000 instances as runs of consecutive vertices (uniform 64-point super-groups, tiles with fewer and
+    # with more than 15 distinct ids: the per-tile id table of msp_cull9.cuh and its global-atomic overflow path)
+    runs255 = np.repeat(rng.integers(0, 256, 2000), rng.integers(5, 130, 2000))[:s.n_points].astype(np.uint16)
+    runs2000 = np.repeat(rng.integers(0, 2001, 9000), rng.integers(1, 20, 9000))
+    runs2000 = np.resize(runs2000, s.n_points).astype(np.uint16)
     for n_obj, ids in ((9, s.instance_ids.copy()), (40, rng.integers(0, 45, s.n_points).astype(np.uint16)),
-                       (100, rng.integers(0, 101, s.n_points).astype(np.uint16))):
+                       (100, rng.integers(0, 101, s.n_points).astype(np.uint16)), (255, runs255), (2000, runs2000)):
         ids[::977] = 60000                                  # out-of-range ids are ignored (treated as "no object")
         sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=ids, num_objects=n_obj)
         sc.render_depth(1)
