@@ -116,8 +116,13 @@ class DeviceScene:
         self.cam = MspCamera(int(image_hw[0]), int(image_hw[1]), int(depth_hw[0]), int(depth_hw[1]), float(depth_scale))
         self.image_hw, self.depth_hw = tuple(image_hw), tuple(depth_hw)
         self.stride = mask_stride_words(self.n)
-        self.instance_ids = None if instance_ids is None else _to_device(
-            np.asarray(instance_ids).astype(np.uint16), torch.uint16, self.device)
+        if instance_ids is None:
+            self.instance_ids = None
+        elif isinstance(instance_ids, torch.Tensor):
+            self.instance_ids = (instance_ids if instance_ids.dtype == torch.uint16 else instance_ids.to(torch.int32).to(torch.uint16)
+                                 ).to(self.device, non_blocking=True).contiguous()
+        else:
+            self.instance_ids = _to_device(np.asarray(instance_ids).astype(np.uint16), torch.uint16, self.device)
         if self.instance_ids is not None and self.perm is not None:
             self.instance_ids = self.instance_ids.view(torch.int16)[self.perm].view(torch.uint16).contiguous()
         self.num_objects = int(num_objects)
@@ -189,12 +194,13 @@ class DeviceScene:
         return (self.mask, xy, z) if materialize else self.mask
 
     @_on_device
-    def project_visibility_objects(self):
+    def project_visibility_objects(self, out_counts: torch.Tensor | None = None):
         """Masks and per-(frame, object) visible counts in one pass (msp_project_visibility_objects)."""
         assert self.depth is not None and self.instance_ids is not None and self.num_objects > 0
         if self.mask is None:
             self.mask = torch.zeros((self.F, self.stride), dtype=torch.int32, device=self.device)
-        counts = torch.empty((self.F, self.num_objects), dtype=torch.int32, device=self.device)
+        counts = out_counts if out_counts is not None else torch.empty((self.F, self.num_objects), dtype=torch.int32, device=self.device)
+        assert counts.dtype == torch.int32 and counts.is_contiguous() and tuple(counts.shape) == (self.F, self.num_objects)
         check(lib.msp_project_visibility_objects(_ptr(self.pts), self.n, self.pts_dtype, self.K_host.ctypes.data,
                                                  _ptr(self.w2c), self.F, _ptr(self.depth), C.byref(self.cam),
                                                  _ptr(self.mask), self.stride, _ptr(self.instance_ids), self.num_objects,

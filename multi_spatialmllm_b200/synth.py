@@ -208,3 +208,27 @@ def make_video(seed: int, n_frames: int = 150, n_tracks: int = 256, n_groups: in
     vis = (cam[..., 2] > 0.1) & (u >= 2) & (u < W - 2) & (v >= 2) & (v < H - 2)
     vis &= rng.random((n_frames, n_tracks)) > 0.1
     return SynthVideo(f"video{seed:05d}", cam, vis, w2c, intr, image_hw)
+
+
+def make_stress_scene(seed: int, n_points: int, n_frames: int, room=(8.0, 8.0, 3.0)) -> SynthScene:
+    """BASELINE.json configs[4] ("synthetic stress"): ``n_points`` uniform random points INSIDE the room volume (no surface
+    structure, no locality in the point order) and independent inward-looking SE(3) poses; no instances.  The depth maps
+    are rendered from the points themselves (msp_zbuffer_render), as in every synthetic config."""
+    rng = np.random.default_rng(seed)
+    rx, ry, rz = room
+    pts = rng.uniform([0.0, 0.0, 0.0], [rx, ry, rz], size=(n_points, 3)).astype(np.float32)
+    inst = np.zeros(n_points, np.uint16)
+    ang = rng.uniform(0, 2 * np.pi)
+    A = np.eye(4)
+    A[:2, :2] = [[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]
+    A[:3, 3] = rng.uniform(-4, 4, 3)
+    A = np.round(A, 6)
+    A_inv = np.linalg.inv(A)
+    eye = rng.uniform([0.5, 0.5, 0.5], [rx - 0.5, ry - 0.5, rz - 0.5], size=(n_frames, 3))
+    tgt = rng.uniform([0.0, 0.0, 0.0], [rx, ry, rz], size=(n_frames, 3))
+    near = np.linalg.norm(tgt - eye, axis=1) < 0.5
+    tgt[near] = np.array([rx / 2, ry / 2, rz / 2])
+    c2w = np.round(A_inv[None] @ look_at_c2w_batch(eye, tgt), 6)
+    c2w[:, 3] = [0, 0, 0, 1]
+    image_ids = [f"{5 * f:05d}" for f in range(n_frames)]
+    return SynthScene(f"stress{seed:04d}_00", pts, inst, 0, A, c2w, SCANNET_K.copy(), image_ids=image_ids)

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE.  The reference needs ``mmengine`` (absent here); a stub
 with the handful of names it touches is planted in ``sys.modules`` and the
-read-only checkout is put on ``sys.path``.  Used by ``tests/golden/make_golden.py``
+read-only checkout — or, on the GPU box, the byte-for-byte copy that
+``oracle/build_ref.py`` staged under ``oracle/_ref`` — is put on ``sys.path``.  Used by ``tests/golden/make_golden.py``
 to produce golden vectors and by the live-reference tests, which skip when the
 checkout is missing (the GPU box has no /root/reference).
 """
@@ -14,7 +15,9 @@ import pickle
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MSP_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py (travels to the GPU box)
+REFERENCE_ROOT = os.environ.get("MSP_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/spatial_engine") else _STAGED)
 
 
 def reference_available() -> bool:

@@ -159,3 +159,35 @@ def test_scene_on_second_device_while_first_is_current():
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][1], out[1][1])
     assert out[0][0].sum() > 0
+
+
+@pytest.mark.gpu
+def test_pair_annotator_public_api_matches_resident_path():
+    """pipeline.PairAnnotator (host buffers in, records out; persistent slots reused across scenes of different sizes)
+    returns exactly what a resident DeviceScene computes."""
+    import torch
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    from multi_spatialmllm_b200.pipeline import HostScene, PairAnnotator
+    ann = PairAnnotator("cuda:0", n_streams=2)
+    jobs = []
+    for seed, n, frames in ((3, 40_000, 12), (4, 9_000, 30), (5, 65_000, 8), (6, 20_000, 16), (7, 50_001, 10)):
+        s = synth.make_scene(seed=seed, n_points=n, n_frames=frames, n_objects=7)
+        sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids, num_objects=s.num_objects)
+        depth = sc.render_depth(1)
+        pairs = torch.arange(frames, dtype=torch.int32).view(-1, 2)
+        sel = torch.arange(frames // 2, dtype=torch.int32) * 977 + 5
+        _, counts = sc.project_visibility_objects()
+        rec = sc.records_to_numpy(sc.pair_annotate(pairs, sel, sel_mode=1))
+        hs = HostScene(torch.from_numpy(s.points), s.K, s.axis_align, torch.from_numpy(s.c2w), depth.cpu(),
+                       torch.from_numpy(s.instance_ids), s.num_objects, s.image_hw, s.depth_hw)
+        if seed % 2:
+            hs = hs.pin()
+        jobs.append((ann.submit(hs, pairs, sel, sel_mode=1), rec, counts.cpu().numpy()))
+    done = ann.drain()
+    assert len(done) == 2                       # three earlier scenes were finished when their slot was reused
+    for h, rec, counts in jobs:
+        assert "slot" not in h
+        for f in ("inter", "uni", "point_id", "permille", "depth_mm", "pix"):
+            np.testing.assert_array_equal(h["records"][f], rec[f])
+        np.testing.assert_array_equal(h["object_counts"], counts)
