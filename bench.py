@@ -625,6 +625,34 @@ def extra_configs(args, dev, rank, world, build_scene, scene_step, barrier, max_
         del scs
         torch.cuda.empty_cache()
 
+    # ---- (ii-b) configs[1] with a ScanNet-like instance count (counting fused for any number of objects)
+    def build_many_objects(i, n_obj):
+        s = synth.make_scene(seed=4242 + rank * 100003 + i, n_points=args.points, n_frames=2 * args.pairs_per_scene, n_objects=n_obj)
+        sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids, num_objects=s.num_objects,
+                         image_hw=s.image_hw, depth_hw=s.depth_hw, device=dev)
+        sc.render_depth(margin_mm=1)
+        sc.c2w_in, sc.A_in = sc.c2w, torch.from_numpy(s.axis_align.reshape(16)).to(dev)
+        sc.pairs = torch.arange(sc.F, dtype=torch.int32, device=dev).view(-1, 2)
+        sc.sel = torch.randint(-2**31, 2**31 - 1, (sc.F // 2,), dtype=torch.int32, device=dev)
+        sc.rec = torch.empty((sc.F // 2, 128), dtype=torch.uint8, device=dev)
+        sc.counts = torch.empty((sc.F, sc.num_objects), dtype=torch.int32, device=dev)
+        sc.mask = torch.empty((sc.F, sc.stride), dtype=torch.int32, device=dev)
+        return sc
+    for n_obj in (12, 150):
+        scs = [build_many_objects(i, n_obj) for i in range(2)]
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in scs]
+
+        def obj_step():
+            for k, sc in enumerate(scs):
+                scene_step(sc, ev3[k])
+        ms = timed(obj_step, steps)
+        torch.cuda.synchronize()
+        out[f"configs1_{n_obj}_objects"] = {"k1_ms_per_launch": sum(a.elapsed_time(b) for a, b in ev3) / len(scs),
+                                           "pairs_per_s": sum_over_ranks(len(scs) * args.pairs_per_scene) / (ms * 1e-3),
+                                           "note": "one launch: masks + per-(frame, object) counts, any object count (per-tile id table)"}
+        del scs
+        torch.cuda.empty_cache()
+
     # ---- (iii) configs[3]-shaped shared-frame scene: N = 200k, F = 375, ALL 70 125 pairs (CFR:176-189), resident and e2e
     f_sh = 375
     iu = np.triu_indices(f_sh, 1)

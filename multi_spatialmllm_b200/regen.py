@@ -6,9 +6,10 @@
 Per scene (one process per GPU, scenes dealt by ``shard.partition_lpt``; no collective on the data path):
   1. upload the scene, project every frame once (K1 + fused object counts)        make_visibility_info.py / compute_object_visibility.py
   2. all-pairs relations (K3)                                                      calculate_frames_relations.py
-  3. sample pairs by overlap bin like the reference's ``sample_dataframe`` (bins (6,35], step 1;
-     camera_movement_engine_train_val.py:29-151 / visual_correspondence_qa_engine_coor_2_coor.py:122-244, simplified to
-     an equal quota per non-empty bin), frames and points for the depth streams (DE-coor:175-199, DC-coor:240-262)
+  3. sample pairs by overlap bin with the exact replica of the reference's ``sample_dataframe``
+     (``pair_engines.sample_rows_by_overlap``: bins [6,35], step 1, quota hand-over from small to large bins;
+     camera_movement_engine_train_val.py:29-151 / visual_correspondence_qa_engine_coor_2_coor.py:122-244), frames and
+     points for the depth streams (DE-coor:175-199, DC-coor:240-262)
   4. annotate in batch (K4) and write JSONL parts in the reference schemas (streams.py)
 Rank 0 gathers the per-rank manifests (shard.gather_manifest) and writes ``manifest.json``.
 """
@@ -23,20 +24,6 @@ import numpy as np
 from . import engine, shard, streams, synth, tables
 
 
-def sample_pairs_by_overlap(overlap: np.ndarray, total: int, lo=6.0, hi=35.0, step=1.0, rng=None) -> np.ndarray:
-    """Indices of pairs with overlap in (lo, hi], an equal share per non-empty ``step``-wide bin."""
-    rng = rng or np.random.default_rng(0)
-    edges = np.arange(lo, hi + step * 0.5, step)
-    which = np.digitize(overlap, edges, right=True)          # bin b <=> edges[b-1] < x <= edges[b]
-    bins = [np.flatnonzero(which == b) for b in range(1, len(edges))]
-    bins = [b for b in bins if len(b)]
-    if not bins or total <= 0:
-        return np.empty(0, np.int64)
-    quota = max(1, total // len(bins))
-    pick = [rng.choice(b, min(quota, len(b)), replace=False) for b in bins]
-    return np.concatenate(pick)[:total]
-
-
 def regenerate_scene(sc: engine.DeviceScene, scene_id: str, image_ids, n_pair_samples: int, n_depth_frames: int, rng):
     """All streams of one scene; returns {stream: [samples]} and the tables."""
     import torch
@@ -48,7 +35,9 @@ def regenerate_scene(sc: engine.DeviceScene, scene_id: str, image_ids, n_pair_sa
     relations = {}
     if len(pairs):
         inter, uni, ov = (t.cpu().numpy() for t in sc.pair_overlap(pairs))
-        sel = sample_pairs_by_overlap(ov, n_pair_samples, rng=rng)
+        from .pair_engines import sample_rows_by_overlap
+        sel = sample_rows_by_overlap(ov, n_pair_samples, 0, overlap_min=6, overlap_max=35, interval=1, np_random=rng,
+                                     log=lambda *a, **k: None)
         chosen = pairs[sel]
         swap = rng.random(len(chosen)) < 0.5                  # random question direction (VC-coor:280-281, CME:163-167)
         chosen[swap] = chosen[swap][:, ::-1]
@@ -107,6 +96,7 @@ def main(argv=None):
     mine = shard.my_shard(costs, rank, world)
     rng = np.random.default_rng(1000 + rank)
     acc, t0 = {}, time.time()
+    n_pairs_done = n_frames_done = 0
     for sid in mine:
         if handler is not None:
             sc, image_ids = tables.device_scene_from_handler(handler, sid, dev)
@@ -116,7 +106,9 @@ def main(argv=None):
                                     num_objects=s.num_objects, device=dev)
             sc.render_depth(1)
             image_ids = s.image_ids
-        out, _ = regenerate_scene(sc, sid, image_ids, args.pairs_per_scene, args.depth_frames_per_scene, rng)
+        out, tabs = regenerate_scene(sc, sid, image_ids, args.pairs_per_scene, args.depth_frames_per_scene, rng)
+        n_frames_done += sc.F
+        n_pairs_done += 0 if not tabs["relations"] else len(tabs["relations"]["pairs"])
         for k, v in out.items():
             acc.setdefault(k, []).extend(v)
     torch.cuda.synchronize()
@@ -124,9 +116,15 @@ def main(argv=None):
     for k, v in acc.items():
         path = shard.part_path(os.path.join(args.out, f"{k}.jsonl"), rank)
         parts[k] = {"path": path, "samples": streams.write_jsonl(v, path)}
-    man = shard.gather_manifest({"rank": rank, "scenes": mine, "seconds": round(time.time() - t0, 2), "parts": parts,
-                                 "samples": sum(p["samples"] for p in parts.values())},
+    secs = max(time.time() - t0, 1e-9)
+    n_samples = sum(p["samples"] for p in parts.values())
+    man = shard.gather_manifest({"rank": rank, "scenes": mine, "seconds": round(secs, 2), "parts": parts, "samples": n_samples,
+                                 "frames": n_frames_done, "pairs_related": n_pairs_done,
+                                 "pairs_per_s": round(n_pairs_done / secs, 1), "frames_per_s": round(n_frames_done / secs, 1),
+                                 "samples_per_s": round(n_samples / secs, 1)},
                                 os.path.join(args.out, "manifest.json"))
+    print(f"[regen rank {rank}] {len(mine)} scenes, {n_frames_done} frames, {n_pairs_done} pairs related, {n_samples} samples in "
+          f"{secs:.1f} s: {n_pairs_done / secs:.0f} pairs/s, {n_samples / secs:.0f} samples/s (JSONL written)", flush=True)
     if rank == 0:
         for k in acc:
             shard.merge_jsonl_parts([m["parts"][k]["path"] for m in man if k in m["parts"]], os.path.join(args.out, f"{k}.jsonl"))

@@ -48,15 +48,15 @@ def _make_io_free_handler(ns, info_path, root, scene, depth):
                       instance_data_root=os.path.join(root, "scannet_instance_data"))
 
 
-def annotate_pairs(ns, handler, scene, n_pairs, rng):
-    """The timed loop: ``n_pairs`` independent pairs (frames 2k, 2k+1) of one scene through the reference's functions."""
+def annotate_pairs(ns, handler, scene, first_pair, n_pairs, rng):
+    """``n_pairs`` independent pairs (frames 2k, 2k+1; k from ``first_pair``) of one scene through the reference's functions."""
     sid = scene.scene_id
     cfr = ns.cfr
     pts = handler.get_scene_points_align(sid)[:, :3]                                     # CFR:143-145
     inst = handler.get_scene_instance_mask(sid)
     obj_points = [set(np.flatnonzero(inst == o + 1).tolist()) for o in range(scene.num_objects)]   # IH:250-261
     done = 0
-    for k in range(n_pairs):
+    for k in range(first_pair, first_pair + n_pairs):
         ids = (scene.image_ids[2 * k], scene.image_ids[2 * k + 1])
         in_bounds, yaw, pitch, pos = {}, {}, {}, {}
         for image_id in ids:                                                             # CFR:152-171
@@ -88,7 +88,8 @@ def annotate_pairs(ns, handler, scene, n_pairs, rng):
 
 def worker(job):
     """One process = one scene, like the reference's Pool-by-scene (make_visibility_info.py:151).
-    job = (seed, n_points, n_pairs, variants) -> {variant: (pairs, seconds)}; scene set-up and file writes are untimed."""
+    job = (seed, n_points, n_pairs, variants) -> {variant: (pairs, seconds)}; scene set-up, file writes and one warm-up
+    pair per variant are untimed (steady-state rate: the per-scene object-point sets of COV:110-118 ARE inside the clock)."""
     seed, n_points, n_pairs, variants = job
     try:
         from threadpoolctl import threadpool_limits
@@ -99,7 +100,7 @@ def worker(job):
     from oracle import geometry as og
     from oracle import ref_layout, ref_shim
     ns = ref_shim.import_reference()
-    s = synth.make_scene(seed=seed, n_points=n_points, n_frames=2 * n_pairs, n_objects=12)
+    s = synth.make_scene(seed=seed, n_points=n_points, n_frames=2 * (n_pairs + 1), n_objects=12)   # + one warm-up pair
     pts = s.points.astype(np.float64)
     H, W = s.image_hw
     E = [og.aligned_pose(s.axis_align, s.c2w[f]) for f in range(s.n_frames)]
@@ -116,8 +117,9 @@ def worker(job):
             else:
                 h = _make_io_free_handler(ns, info_path, root, s, s.depth)
             rng = np.random.default_rng(seed)
+            annotate_pairs(ns, h, s, n_pairs, 1, rng)          # untimed warm-up pair (first-touch pages, lazy imports, BLAS init)
             t0 = time.perf_counter()
-            n = annotate_pairs(ns, h, s, n_pairs, rng)
+            n = annotate_pairs(ns, h, s, 0, n_pairs, rng)
             out[variant] = (n, time.perf_counter() - t0)
     finally:
         shutil.rmtree(root, ignore_errors=True)

@@ -185,7 +185,7 @@ def test_pair_annotator_public_api_matches_resident_path():
             hs = hs.pin()
         jobs.append((ann.submit(hs, pairs, sel, sel_mode=1), rec, counts.cpu().numpy()))
     done = ann.drain()
-    assert len(done) == 2                       # three earlier scenes were finished when their slot was reused
+    assert len(done) == 5                       # (three of them were already finished when their slot was reused)
     for h, rec, counts in jobs:
         assert "slot" not in h
         for f in ("inter", "uni", "point_id", "permille", "depth_mm", "pix"):

@@ -195,3 +195,26 @@ def test_annotation_integers_on_rounding_boundaries():
     assert n_ok > 2000
     if numpy_matches_fixture:
         assert n_off == 0, f"{n_off} boundary values differ although the host inverse order equals the device order"
+
+
+@pytest.mark.gpu
+def test_depth_to_u16_guard_band_equals_float64_definition():
+    """msp_depth_to_u16's float32 fast path + float64 guard band against the all-float64 definition (oracle.depth_to_u16):
+    z values sitting exactly on, and one ulp either side of, millimetre boundaries, far depths that saturate, +inf pixels,
+    and an element count that is not a multiple of 8."""
+    import torch
+    from multi_spatialmllm_b200._lib import check, lib
+    from oracle import geometry as og
+    rng = np.random.default_rng(11)
+    k = rng.integers(1, 70000, 60000)
+    on = (k * 0.001).astype(np.float32)
+    z = np.concatenate([on, np.nextafter(on, np.float32(np.inf)), np.nextafter(on, np.float32(0)),
+                        (k.astype(np.float64) * 0.001).astype(np.float32) + np.float32(1e-7),
+                        rng.uniform(0.0, 70.0, 100003).astype(np.float32),
+                        np.array([np.inf, 0.0, 1e-30, 65.534, 65.535, 65.5351, 1e6, 3e38], np.float32)])
+    z[rng.integers(0, len(z), 5000)] = np.inf
+    zt = torch.from_numpy(z).cuda()
+    for margin in (0, 1, 2, 7):
+        out = torch.empty(len(z), dtype=torch.uint16, device="cuda")
+        check(lib.msp_depth_to_u16(zt.data_ptr(), len(z), margin, 0.001, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        np.testing.assert_array_equal(out.cpu().numpy(), og.depth_to_u16(z, margin))

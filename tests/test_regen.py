@@ -7,15 +7,18 @@ import pytest
 
 
 def test_overlap_bin_sampler_cpu():
-    from multi_spatialmllm_b200 import regen
+    """regen samples pairs with the exact replica of the reference's sample_dataframe (bins [6,35], step 1)."""
+    from multi_spatialmllm_b200.pair_engines import sample_rows_by_overlap
     rng = np.random.default_rng(0)
     ov = np.concatenate([rng.uniform(0, 60, 5000), [np.nan] * 10, [6.0, 35.0, 35.0001]])
-    idx = regen.sample_pairs_by_overlap(ov, 290, rng=np.random.default_rng(1))
-    assert len(idx) <= 290 and len(idx) >= 250 and len(set(idx.tolist())) == len(idx)
-    assert ((ov[idx] > 6.0) & (ov[idx] <= 35.0)).all()                   # (6, 35], NaN never selected
+    idx = sample_rows_by_overlap(ov, 290, 0, overlap_min=6, overlap_max=35, interval=1, np_random=np.random.default_rng(1),
+                                 log=lambda *a, **k: None)
+    assert len(idx) == 290 and len(set(idx.tolist())) == len(idx)
+    assert ((ov[idx] >= 6.0) & (ov[idx] <= 35.0)).all()                  # [6, 35] (include_lowest), NaN never selected
     counts = np.histogram(ov[idx], bins=np.arange(6, 36))[0]
     assert counts.max() - counts.min() <= 2                               # equal share per 1 %-wide bin
-    assert len(regen.sample_pairs_by_overlap(np.array([1.0, 50.0]), 10)) == 0
+    assert len(sample_rows_by_overlap(np.array([1.0, 50.0]), 10, 0, overlap_min=6, overlap_max=35, interval=1,
+                                      log=lambda *a, **k: None)) == 0
 
 
 @pytest.mark.gpu
