@@ -53,7 +53,6 @@ constexpr int kC9Frames = MSP_C9_FRAMES;                          // frames per 
 constexpr int kC9Rounds = kC9Frames / 32;
 static_assert(kC9Frames % 32 == 0 && kC9Frames <= 256, "frames per CTA");
 constexpr int kC9Slots = 16;                                      // local instance-id slots per tile (slot 15 is never used: 15 ids)
-constexpr uint32_t kC9DeferCap = 288;                             // < 32 left over + at most 4 x 64 appended per frame
 #ifndef MSP_C9_MINBLOCKS
 #define MSP_C9_MINBLOCKS 4
 #endif
@@ -64,18 +63,16 @@ constexpr uint32_t kC9DeferCap = 288;                             // < 32 left o
 #define MSP_C9_MASK0_REG 1
 #endif
 #ifndef MSP_C9_LOOP
-#define MSP_C9_LOOP 3       // main loop: 3 pipelined by one super-group within a frame, 0 one super-group at a time, 2 two at a time with the gathers of a pair in flight together
-#endif                      //   (measured slower: at 64 registers the pending state spills, profiles/r2/k1_tuning.md)
-#ifndef MSP_C9_PFL2
-#define MSP_C9_PFL2 0       // > 0: every warp prefetches its rows of the tile's projected bounding box in the depth map of the frame
-#endif                      //   MSP_C9_PFL2 candidate-frames ahead into L2 (prefetch.global.L2), so the gathers find it there
-#ifndef MSP_C9_PF
-#define MSP_C9_PF 0         // 1: stage 1 only PREFETCHES the two depth pixels into L1 (CCTL.E.PF1, no scoreboard) and stage 2 loads them
-#endif
+#define MSP_C9_LOOP 3       // main loop (profiles/r2/k1_tuning.md):
+#endif                      //   3 the frame's candidate super-groups pipelined by one in registers (shipped, 0.431 ms / 2000-frame launch)
+                            //   (tried and removed: gathers as cp.async into a shared-memory ring, compared two items later — no gather
+                            //    stalls left, but +40 % instructions and the LDS/STS traffic saturates the MIO queue: 0.64 ms)
+                            //   0 one super-group at a time, compared right behind its gathers (0.47 ms)
 #ifndef MSP_C9_COEF_PER_SG
 #define MSP_C9_COEF_PER_SG 1   // 1: the 12 packed frame coefficients are re-read from shared memory for every super-group (fewer live registers:
                                //    without it the pending gather state of the pipelined loop spills; measured 0.470 vs 0.535 ms)
 #endif
+constexpr uint32_t kC9DeferCap = 288;                             // < 32 left over + at most 4 x 64 appended per frame
 #if MSP_C9_STRIDED
 #define MSP_C9_SG(warp, k) ((warp) + kC9Warps * (k))
 #else
@@ -108,7 +105,7 @@ struct __align__(16) C9Frame {    // per (tile, frame); 176 bytes = 11 x 16 so t
   float B, B2;                    // common bound of the four in-image forms, and twice that
   unsigned long long dm_biased;   // depth map byte address - 2 * 0x4B000000 (gather index = as_uint(di + 2^23))
   int std_frame;                  // bottom row of w2c is exactly [0,0,0,1]
-  uint32_t bbox;                  // depth-map window the tile can project into: row0 | rows << 9 | line0 << 18 | lines << 22 (128-byte lines), 0 = none
+  uint32_t pad;
 };
 static_assert(sizeof(C9Frame) == 176, "C9Frame layout");
 
@@ -386,30 +383,7 @@ __device__ __forceinline__ void c9_frame_consts(const double* __restrict__ w, co
   c.B = Bf32;
   c.B2 = Bf32 + Bf32;
   c.dm_biased = (unsigned long long)depth_map - 2ull * 0x4B000000ull;
-  // conservative window of depth pixels this tile can land in (prefetch hint only: any value is correct).  Over the tile,
-  // form q stays within dprime +- Aext and Z within [zmin, zmax]; pixel = I / Z.
-  c.bbox = 0u;
-  {
-    const double e0 = fabs(A[0][0]) * ext[0] + fabs(A[0][1]) * ext[1] + fabs(A[0][2]) * ext[2];
-    const double e2 = fabs(A[2][0]) * ext[0] + fabs(A[2][1]) * ext[1] + fabs(A[2][2]) * ext[2];
-    const double e4 = fabs(A[4][0]) * ext[0] + fabs(A[4][1]) * ext[1] + fabs(A[4][2]) * ext[2];
-    const double d0 = A[0][0] * tc[0] + A[0][1] * tc[1] + A[0][2] * tc[2] + A[0][3];
-    const double d2 = A[2][0] * tc[0] + A[2][1] * tc[1] + A[2][2] * tc[2] + A[2][3];
-    const double d4 = A[4][0] * tc[0] + A[4][1] * tc[1] + A[4][2] * tc[2] + A[4][3];
-    const double zmin = d4 - e4, zmax = d4 + e4;
-    if (c.std_frame && zmin > 1e-3 && isfinite(zmax) && isfinite(d0) && isfinite(d2)) {
-      const double xl = fmin((d0 - e0) / zmin, (d0 - e0) / zmax), xh = fmax((d0 + e0) / zmin, (d0 + e0) / zmax);
-      const double yl = fmin((d2 - e2) / zmin, (d2 - e2) / zmax), yh = fmax((d2 + e2) / zmin, (d2 + e2) / zmax);
-      if (xh >= -1.0 && yh >= -1.0 && xl <= dw && yl <= dh) {
-        const int x0 = (int)fmax(floor(xl) - 1.0, 0.0), x1 = (int)fmin(ceil(xh) + 1.0, dw - 1.0);
-        const int y0 = (int)fmax(floor(yl) - 1.0, 0.0), y1 = (int)fmin(ceil(yh) + 1.0, dh - 1.0);
-        const int l0 = (x0 * 2) >> 7, l1 = (x1 * 2) >> 7;   // 128-byte lines within a row (rows are dw * 2 bytes apart; see the prefetch loop)
-        const int rows = y1 - y0 + 1, lines = l1 - l0 + 1;
-        if (rows > 0 && rows < 512 && y0 < 512 && lines > 0 && lines < 1024 && l0 < 16 && lines * rows <= 2048)
-          c.bbox = (uint32_t)y0 | ((uint32_t)rows << 9) | ((uint32_t)l0 << 18) | ((uint32_t)lines << 22);
-      }
-    }
-  }
+  c.pad = 0u;
 }
 
 struct Cull9Params {
@@ -506,12 +480,12 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
         const bool cand = (__fadd_ru(v0, r0) >= nB) && (__fadd_ru(v1, r1) >= nB) && (__fadd_ru(v2, r2) >= nB) && (__fadd_ru(v3, r3) >= nB);
         if (cand) gm |= 1u << k;
       }
-      // zero words are written here, once, by the frame's lane: all of a frame without candidates (it never reaches the
-      // main loop); the pair loop stores per super-group, so there the non-candidate ones of every frame are written too
+      // a frame without candidates never reaches the main loop: its (zero) mask words are written here, by the frame's lane
+      // (in a frame WITH candidates lanes 0..3 of the main loop write all eight words, zero for the non-candidate super-groups)
       uint32_t* zrow = mask0 + (int64_t)fi * p.mask_stride;
 #pragma unroll
       for (int k = 0; k < kC9SgPerWarp; ++k)
-        if ((MSP_C9_LOOP != 2 ? gm == 0u : !((gm >> k) & 1u)) && ((okm >> k) & 1u))
+        if (gm == 0u && ((okm >> k) & 1u))
           *reinterpret_cast<uint2*>(zrow + 2 * MSP_C9_SG(warp, k)) = make_uint2(0u, 0u);
     }
     gmr[r] = gm;
@@ -709,46 +683,13 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
   if (COUNT && lane < kC9SgPerWarp) my_slot = T.sg_slot[my_sg];
   uint32_t s_cnt_lane = smem_u32(&s_cnt[0]) + 4u * (my_slot & (uint32_t)(kC9Slots - 1));
   asm volatile("" : "+r"(s_cnt_lane));
-#if MSP_C9_PFL2 > 0
-  // L2 prefetch of the depth windows this tile projects into, a few candidate frames ahead of the gathers (the capture of the
-  // un-prefetched loop: 55 % of the stall samples wait for a gather, half of the L2 accesses go on to DRAM).  Warp w takes
-  // rows w, w + 8, ... of the window; one lane per row.
-  auto prefetch_window = [&](int fi) {
-    const uint32_t bb = s_c[fi].bbox;
-    const uint32_t rows = (bb >> 9) & 511u, lines = bb >> 22;
-    if (rows == 0u) return;
-    const char* m = reinterpret_cast<const char*>(p.depth + (int64_t)(f0 + fi) * p.depth_stride) + (size_t)((bb >> 18) & 15u) * 128u;
-    for (uint32_t rr = (uint32_t)warp + 8u * (uint32_t)lane; rr < rows; rr += 256u) {
-      const char* a = m + (size_t)((bb & 511u) + rr) * (size_t)(p.g.depth_w * 2);
-      for (uint32_t l = 0; l < lines; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128u));
-    }
-  };
-#endif
 #pragma unroll 1
   for (int r = 0; r < kC9Rounds; ++r) {
     uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
-#if MSP_C9_PFL2 > 0
-    {  // start-up: the first MSP_C9_PFL2 candidate frames of the round
-      uint32_t t = fm;
-#pragma unroll 1
-      for (int i = 0; i < MSP_C9_PFL2 && t != 0u; ++i) {
-        prefetch_window(32 * r + __ffs(t) - 1);
-        t &= t - 1u;
-      }
-    }
-#endif
 #pragma unroll 1
     while (fm != 0u) {
       const int fl = __ffs(fm) - 1;
       fm &= fm - 1u;
-#if MSP_C9_PFL2 > 0
-      {  // the candidate frame MSP_C9_PFL2 places after this one
-        uint32_t t = fm;
-#pragma unroll
-        for (int i = 1; i < MSP_C9_PFL2; ++i) t &= t - 1u;
-        if (t != 0u) prefetch_window(32 * r + __ffs(t) - 1);
-      }
-#endif
       const uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
       const int fi = 32 * r + fl;
       const uint32_t s_cf = smem_u32(&s_c[fi]);
@@ -852,156 +793,6 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
             if (bit && sl == kC9SlotOverflow)
               atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
           }
-        }
-      }
-      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
-    }
-  }
-#else
-  // ---- B + C: frames with candidates in ascending order; within a frame the candidate super-groups are taken two at a time:
-  // project A, issue A's two depth gathers, project B, issue B's gathers, then compare A and B.  The gathers of a pair overlap
-  // each other and B's projection (round-2 capture of the one-at-a-time loop: 46 % of all stall samples sat on the first
-  // consumer of a gather; a pipeline that carried the pending gather over the loop's back-edge made ptxas share the gather's
-  // scoreboard with the loop head's FLO and wait there — profiles/r2/k1_tuning.md).
-  // A lane that does not gather (outside the image, or uncertain) reads pixel 0 of the map (always mapped, L1-resident) and
-  // carries z = +inf ("certainly not visible") or z = NaN ("uncertain"): t = z - d is then +inf / NaN for any d, so
-  // `t < -mz` is false and the uncertainty test !(|t| > mz) is false / true as required — stage 2 needs no predicates.
-  const float finf = __int_as_float(0x7f800000), qnan = __int_as_float(0x7fc00000);
-  uint32_t sgslots = 0;  // COUNT: sg_slot of this warp's four super-groups, one byte each
-  if (COUNT) {
-#pragma unroll
-    for (int k = 0; k < kC9SgPerWarp; ++k) sgslots |= (uint32_t)T.sg_slot[MSP_C9_SG(warp, k)] << (8 * k);
-  }
-  const uint32_t s_cnt0 = smem_u32(&s_cnt[0]);
-
-  struct Pending {
-    f32x2 z;             // (z lo, z hi) or +inf / NaN, see above
-    uint32_t rawl, rawh; // the gathered depth values (u16)
-  };
-  // stage 1 of item (frame constants at s_cf, super-group k): packed float32 projection of 64 points, gathers issued
-  auto project = [&](uint32_t s_cf, int k) -> Pending {
-    const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
-    const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
-    f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
-    lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
-    lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
-    lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
-    const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
-    const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
-    const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
-    const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);  // I0 - dw Z = -Q1 (same rounding as fl(dw Z - I0))
-    const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
-    float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
-    upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
-    // m = min(I0, Q1, I1, Q3); NaN only for empty / non-finite slots: never visible, never queued
-    const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
-    const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
-    const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));  // s = -1/Z (max relative error 2^-23, covered by ct0/ct1)
-    // rint(t) with t = I0 / Z: (-t + 1.5 * 2^23) is an exact integer shift for |t| < 2^22; lanes beyond are never `go`
-    const f32x2 nixm = fma2(I0, s, q.magic2);
-    const f32x2 ix = sub2(q.magic2, nixm);  // = rint(tx), exact
-    const f32x2 fx = fma2(I0, s, ix);       // rint(tx) - tx
-    const f32x2 niym = fma2(I1, s, q.magic2);
-    const f32x2 iy = sub2(q.magic2, niym);
-    const f32x2 fy = fma2(I1, s, iy);
-    // the frame's scalars are re-read from shared memory per item: holding them in registers across the pair made the
-    // compiler spill the gather results (and wait for them) right after the loads
-    f32x2 ct1_2, hct0_2;
-    lds128(s_cf + 128, ct1_2, hct0_2);
-    float Bq, B2q;
-    upk2(lds64(s_cf + 152), Bq, B2q);
-    const float nB = -Bq;
-    const unsigned long long dm = lds64(s_cf + 160);
-    const f32x2 thr = fma2(ct1_2, s, hct0_2);  // 1/2 - ct0 - ct1 / Z
-    float fxl, fxh, fyl, fyh, thl, thh;
-    upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
-    // the reference rounds to the same depth pixel, and the point is certainly inside the image in front of the camera
-    const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
-    const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
-    // gather index: di + 2^23 as an exact float, i.e. the bit pattern 0x4B000000 + di (dm is pre-biased by that constant)
-    const f32x2 ixb = add2(ix, q.two23_2);
-    float ixl, ixh, iyl, iyh;
-    upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
-    const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
-    float dbl, dbh;
-    upk2(dbits, dbl, dbh);
-    const uint32_t bitl = gol ? __float_as_uint(dbl) : 0x4B000000u, bith = goh ? __float_as_uint(dbh) : 0x4B000000u;
-    Pending r;
-    r.z = pk2(gol ? Zl : ((ml >= nB) ? qnan : finf), goh ? Zh : ((mh >= nB) ? qnan : finf));
-    r.rawl = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bitl));
-    r.rawh = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bith));
-    return r;
-  };
-  // stage 2: depth comparison, ballots, mask words, counts, queueing of the uncertain lanes
-  auto finish = [&](const Pending& pd, uint32_t s_cf, int fi, int k) {
-    const f32x2 Bz2 = lds64(s_cf + 144);
-    const uint32_t rowoff = (uint32_t)fi * (uint32_t)p.mask_stride;  // < 2^32: checked by the host
-    // depth: d^ = fl(float(raw) * 0.001f); visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^)
-    const f32x2 d = mul2(add2(pk2(__uint_as_float(0x4B000000u | pd.rawl), __uint_as_float(0x4B000000u | pd.rawh)), q.ntwo23_2), q.fscale2);
-    const f32x2 mz = fma2(q.c36_2, d, Bz2);
-    const f32x2 t = sub2(pd.z, d);
-    float tl, th, mzl, mzh;
-    upk2(t, tl, th), upk2(mz, mzl, mzh);
-    const bool visl = tl < -mzl, vish = th < -mzh;
-    const bool uncl = !(fabsf(tl) > mzl), unch = !(fabsf(th) > mzh);
-    const uint32_t bvl = __ballot_sync(0xffffffffu, visl), bvh = __ballot_sync(0xffffffffu, vish);
-    const uint32_t bu = __ballot_sync(0xffffffffu, uncl | unch);
-    if (lane == 0 && ((okm >> k) & 1u)) *reinterpret_cast<uint2*>(mask0 + (rowoff + 2u * (uint32_t)MSP_C9_SG(warp, k))) = make_uint2(bvl, bvh);
-    if (bu != 0u) {  // rare, warp-uniform: queue the uncertain lanes (lo half first)
-      const uint32_t bul = __ballot_sync(0xffffffffu, uncl), buh = __ballot_sync(0xffffffffu, unch);
-      const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)k << 6) | (uint32_t)lane;
-      if (uncl) s_dq[warp][dq + __popc(bul & lt)] = (uint16_t)code;
-      dq += __popc(bul);
-      if (unch) s_dq[warp][dq + __popc(buh & lt)] = (uint16_t)(code | 32u);
-      dq += __popc(buh);
-    }
-    if (COUNT && (bvl | bvh) != 0u) {
-      const uint32_t slot = (sgslots >> (8 * k)) & 0xffu;  // warp-uniform
-      if (slot < (uint32_t)(kC9Slots - 1)) {
-        if (lane == 0) red_smem_add(s_cnt0 + 4u * ((uint32_t)fi * kC9Slots + slot), (uint32_t)(__popc(bvl) + __popc(bvh)));
-      } else if (slot == kC9SlotMixed) {
-        // the super-group straddles an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
-          const uint32_t sl = T.pt_slot[idx];
-          const bool bit = (((h ? bvh : bvl) >> lane) & 1u) != 0u;
-          const bool act = bit && sl < (uint32_t)(kC9Slots - 1);
-          const uint32_t am = __ballot_sync(0xffffffffu, act);
-          if (act) {
-            const uint32_t grp = __match_any_sync(am, sl);
-            if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
-          }
-          if (bit && sl == kC9SlotOverflow)
-            atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
-        }
-      }
-    }
-  };
-
-#pragma unroll 1
-  for (int r = 0; r < kC9Rounds; ++r) {
-    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
-#pragma unroll 1
-    while (fm != 0u) {
-      const int fl = __ffs(fm) - 1;
-      fm &= fm - 1u;
-      uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
-      const int fi = 32 * r + fl;
-      const uint32_t s_cf = smem_u32(&s_c[fi]);
-#pragma unroll 1
-      while (g != 0u) {
-        const int kA = __ffs(g) - 1;
-        g &= g - 1u;
-        const int kB = __ffs(g) - 1;  // -1: no second candidate
-        g &= g - 1u;                  // 0 & anything = 0
-        const Pending A = project(s_cf, kA);
-        if (kB >= 0) {  // warp-uniform
-          const Pending Bp = project(s_cf, kB);
-          finish(A, s_cf, fi, kA);
-          finish(Bp, s_cf, fi, kB);
-        } else {
-          finish(A, s_cf, fi, kA);
         }
       }
       if (dq >= 32u) flush(32u);  // after this frame's words have been stored

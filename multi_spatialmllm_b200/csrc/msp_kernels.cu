@@ -858,7 +858,9 @@ static int launch_cull9(const FrameLoopParams& p, int dt, cudaStream_t s) {
 
 template <int MODE>
 static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool mat, cudaStream_t s) {
-  if (MODE == MODE_VIS && kstd && !mat && cull_enabled() && cull9_enabled()) return launch_cull9(p, dt, s);
+  // the second-generation kernel gathers depth pixels as aligned 32-bit words (cp.async): every map must start on a 4-byte boundary
+  const bool depth_words_ok = (reinterpret_cast<uintptr_t>(p.depth) & 3u) == 0 && (p.depth_stride & 1) == 0;
+  if (MODE == MODE_VIS && kstd && !mat && cull_enabled() && cull9_enabled() && depth_words_ok) return launch_cull9(p, dt, s);
   if (kstd && !mat && cull_enabled()) {
     // fast path: float32 conservative cull + exact float64 on compacted survivors (msp_cull.cuh)
     const dim3 grid((unsigned)((p.n + kCullTilePoints - 1) / kCullTilePoints),
@@ -945,7 +947,10 @@ extern "C" int msp_project_visibility_objects(const void* pts, int64_t n, int32_
   REQUIRE(n_objects == 0 || (instance_ids && counts), "msp_project_visibility_objects: NULL instance_ids / counts");
   // the second-generation kernel counts any number of objects in the same pass (per-tile local id table); the round-1
   // kernel (MSP_CULL_V9=0) fuses up to kCullMaxObjects and otherwise needs the second launch below
-  const bool fused = n_objects > 0 && (cull9_enabled() || n_objects <= kCullMaxObjects) && n > 0 && K16 != nullptr && k_is_std(K16) && cull_enabled();
+  const bool depth_words_ok = host_cam != nullptr && (reinterpret_cast<uintptr_t>(depth) & 3u) == 0 &&
+                              (((int64_t)host_cam->depth_h * host_cam->depth_w) & 1) == 0;
+  const bool fused = n_objects > 0 && ((cull9_enabled() && depth_words_ok) || n_objects <= kCullMaxObjects) && n > 0 && K16 != nullptr &&
+                     k_is_std(K16) && cull_enabled();
   if (!fused) {  // same result in two launches
     if (int rc = msp_project_visibility(pts, n, pts_dtype, K16, w2c, F, depth, host_cam, mask_bits, mask_stride_words,
                                         nullptr, nullptr, stream)) return rc;

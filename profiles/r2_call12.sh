@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/r2_call12.txt
+for v in v14l3 v14 v14f64; do VC_FRAMES=2000 MSP_LIB=$PWD/build/variants/$v.so python profiles/variant_check.py 2>/dev/null | tail -1 >> gpurun_out/r2_call12.txt; done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_v14.log 2>&1
+echo pytest_v14 rc=$? >> gpurun_out/r2_call12.txt
+VC_FRAMES=2000 ncu --set full --clock-control none --import-source on -k regex:k_frame_cull9 -s 2 -c 1 -o gpurun_out/prof_v14 python profiles/variant_check.py > gpurun_out/prof_v14.log 2>&1
+for v in v14 v14f64; do MSP_LIB=$PWD/build/variants/$v.so python bench.py --scenes 12 --steps 5 --warmup 3 --no-e2e --no-cpu --no-extra 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.readline()); print('$v', 'pairs/s=%.0f' % d['value'], 'k1_ms=%.4f' % d['roofline']['avg_launch_ms'])" >> gpurun_out/r2_call12.txt; done
+cat gpurun_out/r2_call12.txt; tail -3 gpurun_out/r2_pytest_v14.log
