@@ -587,7 +587,7 @@ def extra_configs(args, dev, rank, world, build_scene, scene_step, barrier, max_
         def stress_step():
             for k, sc in enumerate(scs):
                 ev[k][0].record()
-                sc.render_depth(margin_mm=1, chunk=f_st)          # K2: z-buffer splat + float32 -> u16 mm
+                sc.render_depth(margin_mm=1, chunk=f_st, keep_buffers=True)   # K2: z-buffer splat + float32 -> u16 mm
                 ev[k][1].record()
                 sc.project_visibility()                            # K1 (no instances in this config)
                 ev[k][2].record()

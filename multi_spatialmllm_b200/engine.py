@@ -95,7 +95,8 @@ class DeviceScene:
             raise ValueError(f"unsupported point layout {tuple(pts.shape)} {pts.dtype}")
         self.pts = pts.to(self.device, non_blocking=True).contiguous()
         self.n = int(self.pts.shape[0])
-        self.perm = self.inv_perm = None
+        self.perm = self.inv_perm = self._perm_i32 = None
+        self._zb = None
         if reorder == "morton" and self.n > 1:
             xyz = self.pts[:, :3].to(torch.float64)
             finite = torch.isfinite(xyz).all(1, keepdim=True)
@@ -163,13 +164,18 @@ class DeviceScene:
         return zb
 
     @_on_device
-    def render_depth(self, margin_mm: int = 1, chunk: int = 256) -> torch.Tensor:
+    def render_depth(self, margin_mm: int = 1, chunk: int = 256, keep_buffers: bool = False) -> torch.Tensor:
         """Synthetic sensor depth for the scene's own frames (chunked so the fp32 buffer stays small)."""
-        out = torch.empty((self.F, *self.depth_hw), dtype=torch.uint16, device=self.device)
+        out = self.depth if (self.depth is not None and tuple(self.depth.shape) == (self.F, *self.depth_hw)) else \
+            torch.empty((self.F, *self.depth_hw), dtype=torch.uint16, device=self.device)
         px = self.depth_hw[0] * self.depth_hw[1]
+        nz = min(chunk, self.F)
+        zbuf = self._zb if (self._zb is not None and self._zb.shape[0] >= nz) else \
+            torch.empty((nz, *self.depth_hw), dtype=torch.float32, device=self.device)
+        self._zb = zbuf if keep_buffers else None           # the float32 splat buffer (1.2 MB per frame) is only kept on request
         for f0 in range(0, self.F, chunk):
             f1 = min(self.F, f0 + chunk)
-            zb = torch.empty((f1 - f0, *self.depth_hw), dtype=torch.float32, device=self.device)
+            zb = zbuf[:f1 - f0]
             check(lib.msp_zbuffer_render(_ptr(self.pts), self.n, self.pts_dtype, self.K_host.ctypes.data,
                                          self.w2c[f0:].data_ptr(), f1 - f0, C.byref(self.cam), _ptr(zb), _stream()),
                   "msp_zbuffer_render")
@@ -244,8 +250,10 @@ class DeviceScene:
               "msp_pair_annotate")
         if self.perm is not None:                          # point_id (int32 at byte 64) back to the caller's numbering
             pid = rec.view(torch.int32).view(P, 32)[:, 16]
-            ok = pid >= 0
-            pid[ok] = self.perm[pid[ok].long()].to(torch.int32)
+            if self._perm_i32 is None:
+                self._perm_i32 = self.perm.to(torch.int32)
+            # no boolean indexing: that would synchronise the stream (nonzero) in the middle of the step
+            pid.copy_(torch.where(pid >= 0, self._perm_i32[pid.clamp_min(0).long()], pid))
         return rec
 
     @staticmethod

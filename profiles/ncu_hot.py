@@ -4,7 +4,13 @@ rep = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-h = rows[hi]; data = [r for r in rows[hi + 1:] if len(r) == len(h)]
+h = rows[hi]
+data = []
+for r in rows[hi + 1:]:          # first kernel of the report only (a second capture repeats the header)
+    if r and r[0] in ("Address", "Kernel Name"):
+        break
+    if len(r) == len(h):
+        data.append(r)
 ci = {k: i for i, k in enumerate(h)}
 tot = sum(int(r[ci["# Samples"]] or 0) for r in data)
 ex = sum(int(r[ci["Instructions Executed"]] or 0) for r in data)
