@@ -74,7 +74,9 @@ def workload_config(args):
 # clocks sampler (nvidia-smi while the timed region runs)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi -lms 100 in the background; samples are kept with their timestamps so that only those taken while the
+    GPU runs the timed work are used (the tool needs ~1 s to start, the timed region of a default run lasts 0.25 s)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -93,7 +95,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def samples_between(self, t0: float, t1: float) -> int:
+        """Number of samples nvidia-smi has written with a timestamp inside [t0, t1] (wall-clock seconds)."""
+        return len(self._read(t0, t1)[0])
+
+    def _read(self, t0=None, t1=None):
+        import datetime
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 8:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    c, m = float(p[1]), float(p[2])
+                except ValueError:
+                    continue
+                if t0 is not None and not (t0 <= ts <= t1):
+                    continue
+                sm.append(c); mx.append(m)
+                for nm, v in zip(names, p[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        except Exception:
+            pass
+        return sm, mx, reasons
+
+    def stop(self, t0=None, t1=None, note=""):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -102,25 +132,15 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, reasons = self._read(t0, t1)
         try:
-            for ln in open(self.path):
-                p = [x.strip() for x in ln.split(",")]
-                if len(p) < 7:
-                    continue
-                try:
-                    sm.append(float(p[0])); mx.append(float(p[1]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, p[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
             os.unlink(self.path)
         except Exception:
             pass
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        if note:
+            out["note"] = note
         return out
 
 
@@ -391,6 +411,8 @@ def main_gpu(args):
         for k, sc in enumerate(scenes):
             scene_step(sc, None if ev is None else ev[k])
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
@@ -399,18 +421,25 @@ def main_gpu(args):
     r0 = DeviceScene.records_to_numpy(scenes[0].rec)
     assert (r0["uni"] > 0).all() and (r0["point_id"] >= 0).sum() > 0.5 * P, "step produced empty records"
 
-    sampler = ClockSampler(local)
-    sampler.start()
     evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in scenes]
            for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.time()
     e0.record()
     for it in range(args.steps):
         step(evs[it])
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    # clocks DURING the timed work: nvidia-smi (started before the warm-up) samples every 100 ms; a default run's timed region is
+    # shorter than that, so the same steps keep running, untimed, until at least three samples fall inside the loaded window
+    extra_steps = 0
+    while sampler.samples_between(w0, time.time()) < 3 and time.time() - w0 < 6.0:
+        step()
+        torch.cuda.synchronize()
+        extra_steps += 1
+    w1 = time.time()
+    clocks = sampler.stop(w0, w1, note=f"sampled while the timed steps ran and {extra_steps} identical untimed steps right after them")
     elapsed_local = e0.elapsed_time(e1)
     k1_ms = sum(a.elapsed_time(b) for step_ev in evs for (a, b) in step_ev)
     elapsed_ms = max_over_ranks(elapsed_local)
