@@ -62,12 +62,12 @@ constexpr int kC9Slots = 16;                                      // local insta
 #ifndef MSP_C9_MASK0_REG
 #define MSP_C9_MASK0_REG 1
 #endif
-#ifndef MSP_C9_LOOP
-#define MSP_C9_LOOP 3       // main loop (profiles/r2/k1_tuning.md):
-#endif                      //   3 the frame's candidate super-groups pipelined by one in registers (shipped, 0.431 ms / 2000-frame launch)
-                            //   (tried and removed: gathers as cp.async into a shared-memory ring, compared two items later — no gather
-                            //    stalls left, but +40 % instructions and the LDS/STS traffic saturates the MIO queue: 0.64 ms)
-                            //   0 one super-group at a time, compared right behind its gathers (0.47 ms)
+#ifndef MSP_C9_COUNT_GLOBAL
+#define MSP_C9_COUNT_GLOBAL 1  // fused counts: 1 one global RED per (frame, uniform super-group) straight to counts[] (no shared histogram, no
+#endif                         //   end-of-CTA barrier + flush), 0 per-(frame, local slot) counters in 4 KB of shared memory flushed at the end
+#ifndef MSP_C9_HEAD_EARLY
+#define MSP_C9_HEAD_EARLY 1    // 1: the NEXT candidate frame is looked up (ffs, shuffle, address arithmetic) between the issue of a frame's
+#endif                         //   last gathers and their comparison, which otherwise has nothing to overlap with
 #ifndef MSP_C9_COEF_PER_SG
 #define MSP_C9_COEF_PER_SG 1   // 1: the 12 packed frame coefficients are re-read from shared memory for every super-group (fewer live registers:
                                //    without it the pending gather state of the pipelined loop spills; measured 0.470 vs 0.535 ms)
@@ -404,7 +404,7 @@ template <int DT, bool COUNT>
 __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(const Cull9Params q) {
   extern __shared__ __align__(128) unsigned char s_raw[];  // CullTilePrep (without pt_slot when !COUNT)
   __shared__ __align__(16) C9Frame s_c[kC9Frames];
-  __shared__ uint32_t s_cnt[COUNT ? kC9Frames * kC9Slots : 1];  // per (frame, local slot) visible counts
+  __shared__ uint32_t s_cnt[(COUNT && !MSP_C9_COUNT_GLOBAL) ? kC9Frames * kC9Slots : 1];  // per (frame, local slot) visible counts
   __shared__ uint16_t s_dq[kC9Warps][kC9DeferCap];              // (frame in chunk << 8) | (k << 6) | (half << 5) | lane
   __shared__ __align__(8) uint64_t s_bar;
   const CullParams& p = q.p;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
     mbar_init(&s_bar, 1);
     fence_mbar_init();
   }
-  if (COUNT)
+  if (COUNT && !MSP_C9_COUNT_GLOBAL)
     for (int i = tid; i < kC9Frames * kC9Slots; i += kC9Threads) s_cnt[i] = 0u;
   __syncthreads();
   if (tid == 0) {
@@ -510,7 +510,11 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
         atomicOr(p.mask + f * p.mask_stride + word0 + 2 * sg + (sl >> 5), 1u << (sl & 31));
         if (COUNT) {
           const uint32_t s = T.pt_slot[idx];
+#if MSP_C9_COUNT_GLOBAL
+          if (s < (uint32_t)(kC9Slots - 1)) atomicAdd(p.counts + f * p.n_objects + (int)T.slot_id[s] - 1, 1u);
+#else
           if (s < (uint32_t)(kC9Slots - 1)) atomicAdd(&s_cnt[fi * kC9Slots + s], 1u);
+#endif
           else if (s == kC9SlotOverflow) atomicAdd(p.counts + f * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
         }
       }
@@ -527,7 +531,6 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
     __syncwarp();  // the queue may be refilled
   };
 
-#if MSP_C9_LOOP == 3
   // ---- B + C: frames with candidates, ascending.  Within a frame the candidate super-groups are software-pipelined by one:
   // while the two depth gathers of super-group k are in flight the warp projects the next candidate, and only then compares k;
   // the last one of the frame is compared at the frame's end (nothing is carried over the loop's back-edge: ptxas then shares
@@ -540,16 +543,33 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
   const bool my_store = (lane < kC9SgPerWarp) && ((okm >> lane) & 1u);
   uint32_t my_slot = kC9SlotNone;  // COUNT: sg_slot of super-group k = lane (lanes 0..3)
   if (COUNT && lane < kC9SgPerWarp) my_slot = T.sg_slot[my_sg];
+#if MSP_C9_COUNT_GLOBAL
+  // lanes 0..3: counts + (instance id - 1) of the lane's super-group when all its points share one id, else NULL
+  uint32_t* my_cnt = nullptr;
+  if (COUNT && my_slot < (uint32_t)(kC9Slots - 1)) my_cnt = p.counts + (int64_t)f0 * p.n_objects + (int)T.slot_id[my_slot] - 1;
+#else
   uint32_t s_cnt_lane = smem_u32(&s_cnt[0]) + 4u * (my_slot & (uint32_t)(kC9Slots - 1));
   asm volatile("" : "+r"(s_cnt_lane));
+#endif
 #pragma unroll 1
   for (int r = 0; r < kC9Rounds; ++r) {
     uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
+#if MSP_C9_HEAD_EARLY
+    int fl_next = __ffs(fm) - 1;                                              // -1: no candidate frame in this round
+    uint32_t g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
+    fm &= fm - 1u;
+#endif
 #pragma unroll 1
+#if MSP_C9_HEAD_EARLY
+    while (fl_next >= 0) {
+      const int fl = fl_next;
+      const uint32_t g = g_next;
+#else
     while (fm != 0u) {
       const int fl = __ffs(fm) - 1;
       fm &= fm - 1u;
       const uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
+#endif
       const int fi = 32 * r + fl;
       const uint32_t s_cf = smem_u32(&s_c[fi]);
 #if !MSP_C9_COEF_PER_SG
@@ -642,165 +662,55 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
         pz = zsel;
         pk = k;
       }
+#if MSP_C9_HEAD_EARLY
+      // the frame's last gathers are in flight: look the next candidate frame up now
+      fl_next = __ffs(fm) - 1;
+      g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
+      fm &= fm - 1u;
+#endif
       finish();  // g != 0: there is always a pending super-group here
       // lanes 0..3 store their super-group's two words (zero for a non-candidate super-group of this frame) and count them
       if (my_store) *reinterpret_cast<uint2*>(row) = make_uint2(wl, wh);
       if (COUNT) {
         const bool nz = (wl | wh) != 0u;  // only lanes 0..3 can hold a non-zero word
+#if MSP_C9_COUNT_GLOBAL
+        if (nz && my_cnt != nullptr) atomicAdd(my_cnt + (int64_t)fi * p.n_objects, (uint32_t)(__popc(wl) + __popc(wh)));
+#else
         if (nz && my_slot < (uint32_t)(kC9Slots - 1)) red_smem_add(s_cnt_lane + (uint32_t)fi * (4u * kC9Slots), (uint32_t)(__popc(wl) + __popc(wh)));
-        uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
-        // super-groups that straddle an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
-#pragma unroll 1
-        while (mg != 0u) {
-          const int k = __ffs(mg) - 1;
-          mg &= mg - 1u;
-          const uint32_t wvl = __shfl_sync(0xffffffffu, wl, k), wvh = __shfl_sync(0xffffffffu, wh, k);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
-            const uint32_t sl = T.pt_slot[idx];
-            const bool bit = (((h ? wvh : wvl) >> lane) & 1u) != 0u;
-            const bool act = bit && sl < (uint32_t)(kC9Slots - 1);
-            const uint32_t am = __ballot_sync(0xffffffffu, act);
-            if (act) {
-              const uint32_t grp = __match_any_sync(am, sl);
-              if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
-            }
-            if (bit && sl == kC9SlotOverflow)
-              atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
-          }
-        }
-      }
-      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
-    }
-  }
-#elif MSP_C9_LOOP == 0
-  // ---- B + C: frames with candidates, ascending; per candidate super-group the packed float32 evaluation of 64 points
-  // lanes 0..3 own the two mask words (and the counter slot) of the warp's super-group k = lane
-  const int my_sg = MSP_C9_SG(warp, lane & 3);
-  const bool my_store = (lane < kC9SgPerWarp) && ((okm >> lane) & 1u);
-  uint32_t my_slot = kC9SlotNone;  // COUNT: sg_slot of super-group k = lane (lanes 0..3)
-  if (COUNT && lane < kC9SgPerWarp) my_slot = T.sg_slot[my_sg];
-  uint32_t s_cnt_lane = smem_u32(&s_cnt[0]) + 4u * (my_slot & (uint32_t)(kC9Slots - 1));
-  asm volatile("" : "+r"(s_cnt_lane));
-#pragma unroll 1
-  for (int r = 0; r < kC9Rounds; ++r) {
-    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
-#pragma unroll 1
-    while (fm != 0u) {
-      const int fl = __ffs(fm) - 1;
-      fm &= fm - 1u;
-      const uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
-      const int fi = 32 * r + fl;
-      const uint32_t s_cf = smem_u32(&s_c[fi]);
-      f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
-      lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
-      lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
-      lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
-      f32x2 ct1_2, hct0_2, Bz2, BB;
-      lds128(s_cf + 128, ct1_2, hct0_2);
-      lds128(s_cf + 144, Bz2, BB);
-      float Bq, B2q;
-      upk2(BB, Bq, B2q);
-      const float nB = -Bq;
-      const unsigned long long dm = lds64(s_cf + 160);
-      uint32_t* row = mask0 + (int64_t)fi * p.mask_stride + 2 * my_sg;  // lanes 0..3: this frame's two words of super-group k = lane
-      asm volatile("" : "+l"(row));
-      uint32_t wl = 0u, wh = 0u;  // lanes 0..3: those two words
-#pragma unroll
-      for (int k = 0; k < kC9SgPerWarp; ++k) {
-        if (!((g >> k) & 1u)) continue;  // warp-uniform
-        const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
-        const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
-        const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
-        const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
-        const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
-        const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);  // I0 - dw Z = -Q1 (same rounding as fl(dw Z - I0))
-        const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
-        float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
-        upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
-        // m = min(I0, Q1, I1, Q3); NaN only for empty / non-finite slots: never visible, never queued
-        const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
-        const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
-        const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));  // s = -1/Z (max relative error 2^-23, covered by ct0/ct1)
-        // rint(t) with t = I0 / Z: (-t + 1.5 * 2^23) is an exact integer shift for |t| < 2^22; lanes beyond are never `go`
-        const f32x2 nixm = fma2(I0, s, q.magic2);
-        const f32x2 ix = sub2(q.magic2, nixm);  // = rint(tx), exact
-        const f32x2 fx = fma2(I0, s, ix);       // rint(tx) - tx
-        const f32x2 niym = fma2(I1, s, q.magic2);
-        const f32x2 iy = sub2(q.magic2, niym);
-        const f32x2 fy = fma2(I1, s, iy);
-        const f32x2 thr = fma2(ct1_2, s, hct0_2);  // 1/2 - ct0 - ct1 / Z
-        float fxl, fxh, fyl, fyh, thl, thh;
-        upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
-        // the reference rounds to the same depth pixel, and the point is certainly inside the image in front of the camera
-        const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
-        const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
-        // gather index: di + 2^23 as an exact float, i.e. the bit pattern 0x4B000000 + di (dm is pre-biased by that constant)
-        const f32x2 ixb = add2(ix, q.two23_2);
-        float ixl, ixh, iyl, iyh;
-        upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
-        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
-        float dbl, dbh;
-        upk2(dbits, dbl, dbh);
-        uint32_t rawl = 0u, rawh = 0u;
-        if (gol) rawl = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * __float_as_uint(dbl)));
-        if (goh) rawh = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * __float_as_uint(dbh)));
-        // depth: d^ = fl(float(raw) * 0.001f); visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^)
-        const f32x2 d = mul2(add2(pk2(__uint_as_float(0x4B000000u | rawl), __uint_as_float(0x4B000000u | rawh)), q.ntwo23_2), q.fscale2);
-        const f32x2 mz = fma2(q.c36_2, d, Bz2);
-        const f32x2 t = sub2(Zp, d);
-        float tl, th, mzl, mzh;
-        upk2(t, tl, th), upk2(mz, mzl, mzh);
-        const bool visl = gol && (tl < -mzl), vish = goh && (th < -mzh);
-        const bool uncl = gol ? (fabsf(tl) <= mzl) : (ml >= nB);
-        const bool unch = goh ? (fabsf(th) <= mzh) : (mh >= nB);
-        const uint32_t bvl = __ballot_sync(0xffffffffu, visl), bvh = __ballot_sync(0xffffffffu, vish);
-        const uint32_t bu = __ballot_sync(0xffffffffu, uncl | unch);
-        if (lane == k) wl = bvl, wh = bvh;
-        if (bu != 0u) {  // rare, warp-uniform: queue the uncertain lanes (lo half first); flushed after this frame's words are stored
-          const uint32_t bul = __ballot_sync(0xffffffffu, uncl), buh = __ballot_sync(0xffffffffu, unch);
-          const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)k << 6) | (uint32_t)lane;
-          if (uncl) s_dq[warp][dq + __popc(bul & lt)] = (uint16_t)code;
-          dq += __popc(bul);
-          if (unch) s_dq[warp][dq + __popc(buh & lt)] = (uint16_t)(code | 32u);
-          dq += __popc(buh);
-        }
-      }
-      // lanes 0..3 store their super-group's two words (zero for a non-candidate super-group of this frame) and count them
-      if (my_store) *reinterpret_cast<uint2*>(row) = make_uint2(wl, wh);
-      if (COUNT) {
-        const bool nz = (wl | wh) != 0u;  // only lanes 0..3 can hold a non-zero word
-        if (nz && my_slot < (uint32_t)(kC9Slots - 1)) red_smem_add(s_cnt_lane + (uint32_t)fi * (4u * kC9Slots), (uint32_t)(__popc(wl) + __popc(wh)));
-        uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
-        // super-groups that straddle an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
-#pragma unroll 1
-        while (mg != 0u) {
-          const int k = __ffs(mg) - 1;
-          mg &= mg - 1u;
-          const uint32_t wvl = __shfl_sync(0xffffffffu, wl, k), wvh = __shfl_sync(0xffffffffu, wh, k);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
-            const uint32_t sl = T.pt_slot[idx];
-            const bool bit = (((h ? wvh : wvl) >> lane) & 1u) != 0u;
-            const bool act = bit && sl < (uint32_t)(kC9Slots - 1);
-            const uint32_t am = __ballot_sync(0xffffffffu, act);
-            if (act) {
-              const uint32_t grp = __match_any_sync(am, sl);
-              if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
-            }
-            if (bit && sl == kC9SlotOverflow)
-              atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
-          }
-        }
-      }
-      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
-    }
-  }
 #endif
+        uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
+        // super-groups that straddle an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
+#pragma unroll 1
+        while (mg != 0u) {
+          const int k = __ffs(mg) - 1;
+          mg &= mg - 1u;
+          const uint32_t wvl = __shfl_sync(0xffffffffu, wl, k), wvh = __shfl_sync(0xffffffffu, wh, k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
+            const uint32_t sl = T.pt_slot[idx];
+            const bool bit = (((h ? wvh : wvl) >> lane) & 1u) != 0u;
+            const bool act = bit && sl < (uint32_t)(kC9Slots - 1);
+            const uint32_t am = __ballot_sync(0xffffffffu, act);
+            if (act) {
+              const uint32_t grp = __match_any_sync(am, sl);
+#if MSP_C9_COUNT_GLOBAL
+              if (lane == __ffs(grp) - 1)
+                atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)T.slot_id[sl] - 1, (uint32_t)__popc(grp));
+#else
+              if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
+#endif
+            }
+            if (bit && sl == kC9SlotOverflow)
+              atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
+          }
+        }
+      }
+      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
+    }
+  }
   if (dq != 0u) flush(1u);
-  if (COUNT) {
+  if (COUNT && !MSP_C9_COUNT_GLOBAL) {
     __syncthreads();
     for (int i = tid; i < nf * kC9Slots; i += kC9Threads) {
       const uint32_t v = s_cnt[i];
