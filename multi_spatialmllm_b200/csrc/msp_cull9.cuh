@@ -720,4 +720,188 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
   }
 }
 
+// ================================================================================================================
+// K2: z-buffer splat in the same structure (msp_zbuffer_render with standard intrinsics).  NOT in the reference (our definition:
+// per depth pixel the minimum float32(z_ref) over the points that land on it, pixel by the reference's index rule IH:359-366).
+// Classification and the packed float32 projection are K1's; a lane whose depth pixel is certain is QUEUED with that pixel
+// (round 1 recomputed z in float64 inline, i.e. at the lane efficiency of "how many of these 32 points are in view": ~15 % on
+// random clouds), uncertain lanes are queued without one, and the queue is worked off 32 entries at a time with all lanes busy:
+// original coordinates from global memory, z = row 2 of w2c . [x y z 1] in the reference's float64 operation order (certain
+// pixel) or the whole exact projection (uncertain), then one atomicMin on the ordered float bits.
+// ================================================================================================================
+static_assert(kC9Frames <= 32, "k_zbuf_cull9 packs the frame index of a queued point into 5 bits");
+constexpr uint32_t kZ9NoPixel = 0x7ffffu;  // 19-bit pixel field: "uncertain, run the exact projection" (needs depth_w * depth_h < 2^19 - 1)
+
+template <int DT>
+__global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_zbuf_cull9(const Cull9Params q) {
+  extern __shared__ __align__(128) unsigned char s_raw[];  // CullTilePrep without the instance part
+  __shared__ __align__(16) C9Frame s_c[kC9Frames];
+  __shared__ __align__(16) double s_wz[kC9Frames][4];       // row 2 of every frame's w2c (the z form, float64)
+  __shared__ uint32_t s_zq[kC9Warps][96];                   // pixel << 13 | frame in chunk << 8 | k << 6 | half << 5 | lane
+  __shared__ __align__(8) uint64_t s_bar;
+  const CullParams& p = q.p;
+  const CullTilePrep& T = *reinterpret_cast<const CullTilePrep*>(s_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * kC9TilePoints;
+  const int cnt = (int)min((int64_t)kC9TilePoints, p.n - base);
+  const int f0 = blockIdx.y * kC9Frames;
+  const int nf = min(kC9Frames, p.F - f0);
+  const CullTilePrep* gprep = q.prep + blockIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    constexpr uint32_t bytes = (uint32_t)offsetof(CullTilePrep, pt_slot);
+    mbar_arrive_expect_tx(&s_bar, bytes);
+    bulk_g2s(s_raw, gprep, bytes, &s_bar);
+  }
+  if (tid < nf) {
+    const float centre[3] = {__ldg(&gprep->centre[0]), __ldg(&gprep->centre[1]), __ldg(&gprep->centre[2])};
+    const float extf[3] = {__ldg(&gprep->ext[0]), __ldg(&gprep->ext[1]), __ldg(&gprep->ext[2])};
+    const double* w = p.w2c + (int64_t)(f0 + tid) * 16;
+    c9_frame_consts(w, p.K, p.g, centre, extf, nullptr, s_c[tid]);
+    s_wz[tid][0] = w[8], s_wz[tid][1] = w[9], s_wz[tid][2] = w[10], s_wz[tid][3] = w[11];
+  }
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t s_lane = smem_u32(s_raw) + (uint32_t)MSP_C9_SG(warp, 0) * 768u + (uint32_t)lane * 8u;
+  asm volatile("" : "+r"(s_lane));
+  constexpr uint32_t kSgStride = (uint32_t)(MSP_C9_SG(0, 1) - MSP_C9_SG(0, 0)) * 768u;
+
+  // ---- A: classification, lane = frame (as in K1)
+  uint32_t gmr[kC9Rounds];
+#pragma unroll
+  for (int r = 0; r < kC9Rounds; ++r) {
+    const int fi = 32 * r + lane;
+    uint32_t gm = 0u;
+    if (fi < nf) {
+      const C9Frame& c = s_c[fi];
+      const float4 a0l = *reinterpret_cast<const float4*>(&c.a0[0]), a0h = *reinterpret_cast<const float4*>(&c.a0[2]);
+      const float4 a2l = *reinterpret_cast<const float4*>(&c.a2[0]), a2h = *reinterpret_cast<const float4*>(&c.a2[2]);
+      const float4 q1 = *reinterpret_cast<const float4*>(c.q1), q3 = *reinterpret_cast<const float4*>(c.q3);
+      const float nB = -c.B;
+#pragma unroll
+      for (int k = 0; k < kC9SgPerWarp; ++k) {
+        const float4 bc = T.box[MSP_C9_SG(warp, k)][0], bh = T.box[MSP_C9_SG(warp, k)][1];
+        const float v0 = fmaf(a0l.x, bc.x, fmaf(a0l.z, bc.y, fmaf(a0h.x, bc.z, a0h.z)));
+        const float r0 = __fmaf_ru(fabsf(a0l.x), bh.x, __fmaf_ru(fabsf(a0l.z), bh.y, __fmul_ru(fabsf(a0h.x), bh.z)));
+        const float v1 = fmaf(q1.x, bc.x, fmaf(q1.y, bc.y, fmaf(q1.z, bc.z, q1.w)));
+        const float r1 = __fmaf_ru(fabsf(q1.x), bh.x, __fmaf_ru(fabsf(q1.y), bh.y, __fmul_ru(fabsf(q1.z), bh.z)));
+        const float v2 = fmaf(a2l.x, bc.x, fmaf(a2l.z, bc.y, fmaf(a2h.x, bc.z, a2h.z)));
+        const float r2 = __fmaf_ru(fabsf(a2l.x), bh.x, __fmaf_ru(fabsf(a2l.z), bh.y, __fmul_ru(fabsf(a2h.x), bh.z)));
+        const float v3 = fmaf(q3.x, bc.x, fmaf(q3.y, bc.y, fmaf(q3.z, bc.z, q3.w)));
+        const float r3 = __fmaf_ru(fabsf(q3.x), bh.x, __fmaf_ru(fabsf(q3.y), bh.y, __fmul_ru(fabsf(q3.z), bh.z)));
+        const bool cand = (__fadd_ru(v0, r0) >= nB) && (__fadd_ru(v1, r1) >= nB) && (__fadd_ru(v2, r2) >= nB) && (__fadd_ru(v3, r3) >= nB);
+        if (cand) gm |= 1u << k;
+      }
+    }
+    gmr[r] = gm;
+  }
+
+  uint32_t zq = 0;  // warp-uniform fill of s_zq[warp]
+  auto splat = [&](uint32_t e) {  // one queued point on this lane
+    const uint32_t pix = e >> 13;
+    const int fi = (int)((e >> 8) & 31u), k = (int)((e >> 6) & 3u), sl = (int)(e & 63u);
+    const int idx = MSP_C9_SG(warp, k) * 64 + sl;
+    if (idx >= cnt) return;
+    double x, y, z;
+    PtTraits<DT>::load(p.pts, base + idx, x, y, z);
+    unsigned int* zrow = reinterpret_cast<unsigned int*>(p.zbuf + (int64_t)(f0 + fi) * p.depth_stride);
+    if (pix != kZ9NoPixel) {
+      // the pixel is certain; the stored value must be float32(z_ref): z alone, in the reference's operation order (IH:60,63)
+      const double zref = row_dot_h(s_wz[fi], x, y, z);
+      atomicMin(zrow + pix, __float_as_uint(__double2float_rn(zref)));
+    } else {
+      const double* w = p.w2c + (int64_t)(f0 + fi) * 16;
+      const Proj pr = (s_c[fi].std_frame != 0) ? project_exact<true>(w, p.K, x, y, z) : project_exact<false>(w, p.K, x, y, z);
+      if (in_image(pr, p.g) && pr.z > 0.0) atomicMin(zrow + depth_index(pr, p.g), __float_as_uint(__double2float_rn(pr.z)));
+    }
+  };
+  auto flush = [&](uint32_t keep_below) {
+    __syncwarp();
+    while (zq >= keep_below && zq != 0u) {
+      const uint32_t nb = zq < 32u ? zq : 32u;
+      if (lane < nb) splat(s_zq[warp][zq - nb + lane]);
+      zq -= nb;
+    }
+    __syncwarp();
+  };
+
+#pragma unroll 1
+  for (int r = 0; r < kC9Rounds; ++r) {
+    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
+#pragma unroll 1
+    while (fm != 0u) {
+      const int fl = __ffs(fm) - 1;
+      fm &= fm - 1u;
+      uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
+      const int fi = 32 * r + fl;
+      const uint32_t s_cf = smem_u32(&s_c[fi]);
+      f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw, ct1_2, hct0_2, Bz2, BB;
+      lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
+      lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
+      lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
+      lds128(s_cf + 128, ct1_2, hct0_2);
+      lds128(s_cf + 144, Bz2, BB);
+      float Bq, B2q;
+      upk2(BB, Bq, B2q);
+      const float nB = -Bq;
+#pragma unroll 1
+      while (g != 0u) {
+        const int k = __ffs(g) - 1;
+        g &= g - 1u;
+        const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
+        const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
+        const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
+        const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
+        const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
+        const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);
+        const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
+        float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
+        upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
+        const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
+        const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
+        const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));
+        const f32x2 nixm = fma2(I0, s, q.magic2);
+        const f32x2 ix = sub2(q.magic2, nixm);
+        const f32x2 fx = fma2(I0, s, ix);
+        const f32x2 niym = fma2(I1, s, q.magic2);
+        const f32x2 iy = sub2(q.magic2, niym);
+        const f32x2 fy = fma2(I1, s, iy);
+        const f32x2 thr = fma2(ct1_2, s, hct0_2);
+        float fxl, fxh, fyl, fyh, thl, thh;
+        upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
+        const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
+        const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
+        const bool uncl = !gol && (ml >= nB), unch = !goh && (mh >= nB);
+        const f32x2 ixb = add2(ix, q.two23_2);
+        float ixl, ixh, iyl, iyh;
+        upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
+        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
+        float dbl, dbh;
+        upk2(dbits, dbl, dbh);
+        // queue every lane that may land on a pixel: certain ones with the pixel, uncertain ones with the "no pixel" mark
+        const uint32_t bql = __ballot_sync(0xffffffffu, gol | uncl), bqh = __ballot_sync(0xffffffffu, goh | unch);
+        const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)k << 6) | (uint32_t)lane;
+        const uint32_t el = ((gol ? (__float_as_uint(dbl) - 0x4B000000u) : kZ9NoPixel) << 13) | code;
+        const uint32_t eh = ((goh ? (__float_as_uint(dbh) - 0x4B000000u) : kZ9NoPixel) << 13) | code | 32u;
+        // (splatting a dense half in place instead of queueing it was measured 3.5x slower on mesh-ordered clouds: divergent
+        //  float64 code inside the projection loop; profiles/r2/k1_tuning.md)
+        if (gol | uncl) s_zq[warp][zq + __popc(bql & lt)] = el;
+        zq += __popc(bql);
+        if (goh | unch) s_zq[warp][zq + __popc(bqh & lt)] = eh;
+        zq += __popc(bqh);
+        if (zq >= 32u) flush(32u);
+      }
+    }
+  }
+  if (zq != 0u) flush(1u);
+}
+
 }  // namespace msp

@@ -793,27 +793,29 @@ static bool cull9_enabled() {
   return !(e != nullptr && e[0] == '0');
 }
 
+// Keep the stream-ordered workspace of K1 / K2 in the device's default memory pool between calls (the default release threshold
+// of 0 hands it back to the driver at every synchronisation, and the next call pays a real allocation).
+static void keep_workspace_pool() {
+  static thread_local int pool_ready_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (pool_ready_dev != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = 1ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_ready_dev = dev;
+  }
+}
+
 // K1 second generation (msp_cull9.cuh): prepare pass into a stream-ordered workspace, then the main kernel.
 static int launch_cull9(const FrameLoopParams& p, int dt, cudaStream_t s) {
   const unsigned tiles = (unsigned)((p.n + kC9TilePoints - 1) / kC9TilePoints);
   const dim3 grid(tiles, (unsigned)((p.F + kC9Frames - 1) / kC9Frames));
   REQUIRE(grid.y <= 65535u, "too many frames in one call");
   CullTilePrep* prep = nullptr;
-  {
-    // keep the workspace in the device's default memory pool between calls (the default threshold of 0 hands it back to
-    // the driver at every synchronisation, and the next call pays a real allocation)
-    static thread_local int pool_ready_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (pool_ready_dev != dev) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = 1ull << 30;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      pool_ready_dev = dev;
-    }
-  }
+  keep_workspace_pool();
   if (cudaMallocAsync(reinterpret_cast<void**>(&prep), sizeof(CullTilePrep) * (size_t)tiles, s) != cudaSuccess)
     return check_launch("msp_project_visibility(workspace)");
   const bool count = p.counts != nullptr;
@@ -856,8 +858,52 @@ static int launch_cull9(const FrameLoopParams& p, int dt, cudaStream_t s) {
   return rc;
 }
 
+// K2 second generation (k_zbuf_cull9): prepare pass + packed projection + batched float64 splat.
+static int launch_zbuf9(const FrameLoopParams& p, int dt, cudaStream_t s) {
+  const unsigned tiles = (unsigned)((p.n + kC9TilePoints - 1) / kC9TilePoints);
+  const dim3 grid(tiles, (unsigned)((p.F + kC9Frames - 1) / kC9Frames));
+  REQUIRE(grid.y <= 65535u, "too many frames in one call");
+  CullTilePrep* prep = nullptr;
+  keep_workspace_pool();
+  if (cudaMallocAsync(reinterpret_cast<void**>(&prep), sizeof(CullTilePrep) * (size_t)tiles, s) != cudaSuccess)
+    return check_launch("msp_zbuffer_render(workspace)");
+  Cull9Params q{};
+  CullParams& c = q.p;
+  c.pts = p.pts, c.n = p.n, c.w2c = p.w2c, c.F = p.F, c.depth = nullptr, c.zbuf = p.zbuf;
+  c.depth_stride = p.depth_stride, c.K = p.K, c.g = p.g;
+  q.prep = prep;
+  const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h;
+  auto dup = [](float v) {
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    return (unsigned long long)b | ((unsigned long long)b << 32);
+  };
+  q.nfdw2 = dup(-fdw), q.nfdh2 = dup(-fdh), q.fdw2 = dup(fdw);
+  q.magic2 = dup(12582912.0f), q.two23_2 = dup(8388608.0f), q.ntwo23_2 = dup(-8388608.0f);
+  q.xclip = (fdw - 1.0f) + 8388608.0f, q.yclip = fdh - 1.0f;
+  constexpr int smem = (int)offsetof(CullTilePrep, pt_slot);
+  switch (dt) {
+    case 0:
+      k_cull_prepare<0><<<tiles, kC9Threads, 0, s>>>(p.pts, p.n, nullptr, 0, prep);
+      k_zbuf_cull9<0><<<grid, kC9Threads, smem, s>>>(q);
+      break;
+    case 1:
+      k_cull_prepare<1><<<tiles, kC9Threads, 0, s>>>(p.pts, p.n, nullptr, 0, prep);
+      k_zbuf_cull9<1><<<grid, kC9Threads, smem, s>>>(q);
+      break;
+    default:
+      k_cull_prepare<2><<<tiles, kC9Threads, 0, s>>>(p.pts, p.n, nullptr, 0, prep);
+      k_zbuf_cull9<2><<<grid, kC9Threads, smem, s>>>(q);
+      break;
+  }
+  int rc = check_launch("k_zbuf_cull9");
+  if (cudaFreeAsync(prep, s) != cudaSuccess && rc == MSP_OK) rc = check_launch("msp_zbuffer_render(workspace free)");
+  return rc;
+}
+
 template <int MODE>
 static int launch_frame_loop(const FrameLoopParams& p, int dt, bool kstd, bool mat, cudaStream_t s) {
+  if (MODE == MODE_ZBUF && kstd && cull_enabled() && cull9_enabled() && p.depth_stride < (int64_t)kZ9NoPixel) return launch_zbuf9(p, dt, s);
   // the second-generation kernel gathers depth pixels as aligned 32-bit words (cp.async): every map must start on a 4-byte boundary
   const bool depth_words_ok = (reinterpret_cast<uintptr_t>(p.depth) & 3u) == 0 && (p.depth_stride & 1) == 0;
   if (MODE == MODE_VIS && kstd && !mat && cull_enabled() && cull9_enabled() && depth_words_ok) return launch_cull9(p, dt, s);

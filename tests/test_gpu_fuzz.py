@@ -218,3 +218,37 @@ def test_depth_to_u16_guard_band_equals_float64_definition():
         out = torch.empty(len(z), dtype=torch.uint16, device="cuda")
         check(lib.msp_depth_to_u16(zt.data_ptr(), len(z), margin, 0.001, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         np.testing.assert_array_equal(out.cpu().numpy(), og.depth_to_u16(z, margin))
+
+
+@pytest.mark.gpu
+def test_cull9_nonstandard_frames_and_unaligned_depth(monkeypatch):
+    """Corners of the round-2 K1 (msp_cull9.cuh): a pose whose inverse has a non-[0,0,0,1] bottom row (every lane goes through the
+    deferred exact path), depth maps that start on an odd 2-byte boundary and depth maps with an odd pixel count (both take the
+    round-1 kernel: the new one gathers aligned 32-bit words) — all against the all-float64 reference-order kernel."""
+    import torch
+    from multi_spatialmllm_b200 import synth
+    from multi_spatialmllm_b200.engine import DeviceScene
+    s = synth.make_scene(seed=31, n_points=37_777, n_frames=7, n_objects=5)
+    c2w = s.c2w.copy()
+    c2w[2, 3, 3] = 2.0                                   # homogeneous scale: w2c bottom row becomes [0,0,0,0.5]
+    c2w[5, 3, :] = [0.0, 1e-3, 0.0, 1.0]                 # a perspective row
+    for dhw in ((480, 640), (37, 51)):                   # 37 * 51 is odd: depth_stride is odd
+        sc = DeviceScene(s.points, s.K, c2w, axis_align=s.axis_align, instance_ids=s.instance_ids, num_objects=s.num_objects,
+                         depth_hw=dhw)
+        depth = sc.render_depth(1).clone()
+        monkeypatch.setenv("MSP_DISABLE_CULL", "1")
+        sc.project_visibility()
+        ref_mask = sc.mask.cpu().numpy().copy()
+        ref_cnt = sc.object_counts().cpu().numpy()
+        monkeypatch.setenv("MSP_DISABLE_CULL", "0")
+        for shift in (0, 1):                             # shift 1: the maps start 2 bytes off a 4-byte boundary
+            big = torch.zeros(depth.numel() + 8, dtype=torch.uint16, device="cuda")
+            view = big[shift:shift + depth.numel()].view(depth.shape)
+            view.copy_(depth)
+            assert (view.data_ptr() % 4 == 0) == (shift == 0)
+            sc.depth = view
+            sc.mask.fill_(-1)
+            _, cnt = sc.project_visibility_objects()
+            np.testing.assert_array_equal(sc.mask.cpu().numpy(), ref_mask)
+            np.testing.assert_array_equal(cnt.cpu().numpy(), ref_cnt)
+        assert ref_mask.any()
