@@ -711,6 +711,41 @@ def extra_configs(args, dev, rank, world, build_scene, scene_step, barrier, max_
     out["shared_frame_375"]["e2e_d2h_bytes_per_scene"] = h["d2h_bytes"]
     del sc_sh, ann, hs
     torch.cuda.empty_cache()
+
+    # ---- (iv) the regeneration driver on configs[3]-shaped scenes: K1 + all-pairs relations + the exact
+    #          sample_dataframe replica + the batch writers of four streams, JSONL written to a scratch directory (wall clock)
+    import shutil
+    from multi_spatialmllm_b200 import regen, streams
+    tmp = tempfile.mkdtemp(prefix="msp_regen_")
+    try:
+        rng = np.random.default_rng(4321 + rank)
+        n_sc, frames_done, pairs_done, samples = 2, 0, 0, 0
+        scs = []
+        for i in range(n_sc):
+            s = synth.make_scene(seed=8800 + rank * 17 + i, n_points=args.points, n_frames=f_sh, n_objects=12)
+            sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids, num_objects=s.num_objects, device=dev)
+            sc.render_depth(1)
+            scs.append((s, sc))
+        barrier()
+        t0 = time.perf_counter()
+        for s, sc in scs:
+            res, tabs = regen.regenerate_scene(sc, s.scene_id, s.image_ids, 200, 32, rng)
+            frames_done += sc.F
+            pairs_done += 0 if not tabs["relations"] else len(tabs["relations"]["pairs"])
+            for k, v in res.items():
+                samples += streams.write_jsonl(v, os.path.join(tmp, f"{k}.part-{rank:05d}.jsonl"))
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out["regen"] = {"scenes_per_gpu": n_sc, "frames_per_scene": f_sh, "points": args.points,
+                        "pairs_related_per_s": sum_over_ranks(pairs_done) / dt, "samples_per_s": sum_over_ranks(samples) / dt,
+                        "frames_per_s": sum_over_ranks(frames_done) / dt, "seconds": dt,
+                        "note": ("regen.regenerate_scene per scene: masks + counts, all-pairs relations, 200 pairs drawn by the reference's "
+                                 "overlap-bin sampler, visual_correspondence + 9 camera_movement question types + depth_estimation / "
+                                 "depth_comparison samples, JSONL to local scratch; wall clock, host formatting included")}
+        del scs
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    torch.cuda.empty_cache()
     return out
 
 

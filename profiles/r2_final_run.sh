@@ -16,4 +16,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 compute-sanitizer --tool memcheck python __graft_entry__.py smoke > gpurun_out/r2_sanitizer_memcheck_smoke.log 2>&1
 compute-sanitizer --tool racecheck python __graft_entry__.py smoke > gpurun_out/r2_sanitizer_racecheck_smoke.log 2>&1
 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_configs.py -m gpu -x -q > gpurun_out/r2_sanitizer_memcheck_pytest.log 2>&1
-tail -3 gpurun_out/r2_sanitizer_memcheck_smoke.log gpurun_out/r2_sanitizer_racecheck_smoke.log gpurun_out/r2_sanitizer_memcheck_pytest.log
+for f in gpurun_out/r2_sanitizer_*.log; do tail -n 3 "$f"; done
