@@ -112,6 +112,29 @@ def device_relations():
 device_relations()
 out["relations_device_s"], _ = wall(device_relations)
 
+
+# ---- a stream of scenes through the visibility table writer (what tables.run_visibility_split does per scene): the single
+#      reference-shaped file (one encode thread, overlapped with the next scene's kernels) vs the dataset layout with 8 encode threads
+def stream_scenes(writers, n_scenes=8):
+    import shutil
+    path = os.path.join(tmp, f"vis_stream_{writers}.parquet")
+    w = tables._ParquetStream(path, writers=writers)
+    t0 = time.perf_counter()
+    for k in range(n_scenes):
+        sc.project_visibility()
+        w.write(tables.visibility_arrow_table(sc, f"scene{k:04d}_00", ids))
+    rows = w.close()
+    dt = time.perf_counter() - t0
+    if os.path.isdir(path):
+        shutil.rmtree(path)
+    else:
+        os.remove(path)
+    return n_scenes * F / dt, rows
+
+
+stream_scenes(1, 2)
+out["visibility_stream_frames_per_s"] = {"single_file_1_writer": stream_scenes(1)[0], "dataset_8_writers": stream_scenes(8)[0]}
+
 # ---- dict path (GPU geometry, Python formatting) — what this repo did before the device formatter
 def dict_visibility():
     tab = engine.process_scene_visibility(sc, ids)

@@ -203,3 +203,22 @@ def test_parquet_stream_cpu(tmp_path):
     with pytest.raises(ValueError):
         tables._check_json_safe(['quo"te'])
     tables._check_json_safe(["00005", "frame_12", "a b"])
+
+
+def test_parquet_stream_dataset_layout_reads_like_the_single_file(tmp_path):
+    """_ParquetStream(writers > 1): a *.parquet directory of per-scene files whose rows, read through the path the way
+    VisibilityInfoHandler does (pd.read_parquet, IH:451-460), equal the single file's rows in the same order."""
+    import pandas as pd
+    import pyarrow as pa
+    from multi_spatialmllm_b200 import tables
+    tabs = [pa.table({"key": [f"scene{k:04d}_00:point_to_images:{i}" for i in range(50 + k)],
+                      "values": [str(list(range(i % 7))) for i in range(50 + k)]}) for k in range(13)]
+    one, many = str(tmp_path / "one.parquet"), str(tmp_path / "many.parquet")
+    w1, wn = tables._ParquetStream(one), tables._ParquetStream(many, writers=4)
+    for t in tabs:
+        w1.write(t)
+        wn.write(t)
+    assert w1.close() == wn.close() == sum(t.num_rows for t in tabs)
+    assert os.path.isfile(one) and os.path.isdir(many) and len(os.listdir(many)) == 13
+    a, b = pd.read_parquet(one), pd.read_parquet(many)
+    assert a["key"].tolist() == b["key"].tolist() and a["values"].tolist() == b["values"].tolist()
