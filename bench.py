@@ -726,6 +726,7 @@ def extra_configs(args, dev, rank, world, build_scene, scene_step, barrier, max_
             sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=s.instance_ids, num_objects=s.num_objects, device=dev)
             sc.render_depth(1)
             scs.append((s, sc))
+        regen.regenerate_scene(scs[0][1], scs[0][0].scene_id, scs[0][0].image_ids, 200, 32, np.random.default_rng(1))   # untimed: lazy imports
         barrier()
         t0 = time.perf_counter()
         for s, sc in scs:
