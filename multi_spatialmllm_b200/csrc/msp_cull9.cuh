@@ -18,14 +18,17 @@
 //     frames at once (no ballot, no per-frame head), leaves a 4-bit candidate mask per (warp, frame) in a register, and the
 //     lanes write the all-zero mask words of their non-candidate (frame, super-group)s directly.  The main loop then only
 //     visits frames that have a candidate (ffs over a ballot), in ascending frame order (depth-map locality in L1/L2).
-//   * each candidate super-group's two mask words are stored by lane 0 straight from the ballots (no word shuffling);
+//   * within a frame the candidate super-groups are software-pipelined by one: the comparison of super-group k runs after
+//     the projection of the next candidate, so that its two depth gathers have a whole projection to land; lanes 0..3
+//     collect the frame's eight mask words and store them once per frame;
 //   * uncertain lanes are queued per warp ACROSS frames and the exact float64 path runs on 32 of them at a time, OR-ing
 //     visible bits into the stored words (the validated round-1 "deferred exact" variant, now the only exact path — a
 //     non-standard frame simply queues every lane and becomes the all-float64 kernel at full lane utilisation);
 //   * fused per-(frame, object) counting works for ANY number of objects: a tile of 2 048 consecutive points touches few
-//     instances, so the prepare pass gives each tile a 15-entry local id table; counts are accumulated per (frame, local
-//     slot) in 2 KB of shared memory (was 8 KB for <= 63 global ids) and flushed with one atomic per non-zero counter.  Ids
-//     that do not fit the table (> 15 distinct in one tile, e.g. shuffled clouds) are counted with global atomics.
+//     instances, so the prepare pass gives each tile a 15-entry table of its ids and marks every super-group whose points
+//     share one id; such a super-group adds its popcount to counts[frame][id] with ONE global RED per frame (no shared
+//     histogram, no end-of-CTA barrier), mixed ones aggregate by id within the warp first; ids that do not fit the table
+//     (> 15 distinct in one tile, e.g. shuffled clouds) are looked up in the caller's id array.
 //
 // Bit-identical to k_frame_loop (all-float64) and to the round-1 kernel by construction: a float32 decision is only taken
 // when the bounds prove it; the packed operations are IEEE single roundings per half in the same association order as the
@@ -59,15 +62,6 @@ constexpr int kC9Slots = 16;                                      // local insta
 #ifndef MSP_C9_STRIDED
 #define MSP_C9_STRIDED 1       // 1: warp w owns super-groups w, w+8, w+16, w+24 (even work per warp), 0: 4w .. 4w+3
 #endif
-#ifndef MSP_C9_MASK0_REG
-#define MSP_C9_MASK0_REG 1
-#endif
-#ifndef MSP_C9_COUNT_GLOBAL
-#define MSP_C9_COUNT_GLOBAL 1  // fused counts: 1 one global RED per (frame, uniform super-group) straight to counts[] (no shared histogram, no
-#endif                         //   end-of-CTA barrier + flush), 0 per-(frame, local slot) counters in 4 KB of shared memory flushed at the end
-#ifndef MSP_C9_HEAD_EARLY
-#define MSP_C9_HEAD_EARLY 1    // 1: the NEXT candidate frame is looked up (ffs, shuffle, address arithmetic) between the issue of a frame's
-#endif                         //   last gathers and their comparison, which otherwise has nothing to overlap with
 #ifndef MSP_C9_COEF_PER_SG
 #define MSP_C9_COEF_PER_SG 1   // 1: the 12 packed frame coefficients are re-read from shared memory for every super-group (fewer live registers:
                                //    without it the pending gather state of the pipelined loop spills; measured 0.470 vs 0.535 ms)
@@ -144,10 +138,6 @@ __device__ __forceinline__ f32x2 lds64(uint32_t addr) {
 }
 __device__ __forceinline__ void lds128(uint32_t addr, f32x2& a, f32x2& b) {
   asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
-}
-
-__device__ __forceinline__ void red_smem_add(uint32_t addr, uint32_t v) {
-  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // ================================================================================================================
@@ -404,7 +394,6 @@ template <int DT, bool COUNT>
 __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(const Cull9Params q) {
   extern __shared__ __align__(128) unsigned char s_raw[];  // CullTilePrep (without pt_slot when !COUNT)
   __shared__ __align__(16) C9Frame s_c[kC9Frames];
-  __shared__ uint32_t s_cnt[(COUNT && !MSP_C9_COUNT_GLOBAL) ? kC9Frames * kC9Slots : 1];  // per (frame, local slot) visible counts
   __shared__ uint16_t s_dq[kC9Warps][kC9DeferCap];              // (frame in chunk << 8) | (k << 6) | (half << 5) | lane
   __shared__ __align__(8) uint64_t s_bar;
   const CullParams& p = q.p;
@@ -421,8 +410,6 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
     mbar_init(&s_bar, 1);
     fence_mbar_init();
   }
-  if (COUNT && !MSP_C9_COUNT_GLOBAL)
-    for (int i = tid; i < kC9Frames * kC9Slots; i += kC9Threads) s_cnt[i] = 0u;
   __syncthreads();
   if (tid == 0) {
     constexpr uint32_t bytes = COUNT ? (uint32_t)sizeof(CullTilePrep) : (uint32_t)offsetof(CullTilePrep, pt_slot);
@@ -445,9 +432,7 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
   for (int k = 0; k < kC9SgPerWarp; ++k)
     if (word0 + 2 * MSP_C9_SG(warp, k) < p.mask_stride) okm |= 1u << k;
   uint32_t* mask0 = p.mask + (int64_t)f0 * p.mask_stride + word0;  // + fi * mask_stride + 2 * sg
-#if MSP_C9_MASK0_REG
   asm volatile("" : "+l"(mask0));  // kept in a register pair instead of being rebuilt from blockIdx at every store
-#endif
   // this lane's points of super-group k are at shared address s_lane + kSgStride k (+0 x, +256 y, +512 z); the address is made
   // opaque so that it stays in a register instead of being re-derived from the thread id at every use
   uint32_t s_lane = smem_u32(s_raw) + (uint32_t)MSP_C9_SG(warp, 0) * 768u + (uint32_t)lane * 8u;
@@ -510,11 +495,7 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
         atomicOr(p.mask + f * p.mask_stride + word0 + 2 * sg + (sl >> 5), 1u << (sl & 31));
         if (COUNT) {
           const uint32_t s = T.pt_slot[idx];
-#if MSP_C9_COUNT_GLOBAL
           if (s < (uint32_t)(kC9Slots - 1)) atomicAdd(p.counts + f * p.n_objects + (int)T.slot_id[s] - 1, 1u);
-#else
-          if (s < (uint32_t)(kC9Slots - 1)) atomicAdd(&s_cnt[fi * kC9Slots + s], 1u);
-#endif
           else if (s == kC9SlotOverflow) atomicAdd(p.counts + f * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
         }
       }
@@ -543,33 +524,19 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
   const bool my_store = (lane < kC9SgPerWarp) && ((okm >> lane) & 1u);
   uint32_t my_slot = kC9SlotNone;  // COUNT: sg_slot of super-group k = lane (lanes 0..3)
   if (COUNT && lane < kC9SgPerWarp) my_slot = T.sg_slot[my_sg];
-#if MSP_C9_COUNT_GLOBAL
   // lanes 0..3: counts + (instance id - 1) of the lane's super-group when all its points share one id, else NULL
   uint32_t* my_cnt = nullptr;
   if (COUNT && my_slot < (uint32_t)(kC9Slots - 1)) my_cnt = p.counts + (int64_t)f0 * p.n_objects + (int)T.slot_id[my_slot] - 1;
-#else
-  uint32_t s_cnt_lane = smem_u32(&s_cnt[0]) + 4u * (my_slot & (uint32_t)(kC9Slots - 1));
-  asm volatile("" : "+r"(s_cnt_lane));
-#endif
 #pragma unroll 1
   for (int r = 0; r < kC9Rounds; ++r) {
     uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
-#if MSP_C9_HEAD_EARLY
     int fl_next = __ffs(fm) - 1;                                              // -1: no candidate frame in this round
     uint32_t g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
     fm &= fm - 1u;
-#endif
 #pragma unroll 1
-#if MSP_C9_HEAD_EARLY
     while (fl_next >= 0) {
       const int fl = fl_next;
       const uint32_t g = g_next;
-#else
-    while (fm != 0u) {
-      const int fl = __ffs(fm) - 1;
-      fm &= fm - 1u;
-      const uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
-#endif
       const int fi = 32 * r + fl;
       const uint32_t s_cf = smem_u32(&s_c[fi]);
 #if !MSP_C9_COEF_PER_SG
@@ -662,22 +629,16 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
         pz = zsel;
         pk = k;
       }
-#if MSP_C9_HEAD_EARLY
       // the frame's last gathers are in flight: look the next candidate frame up now
       fl_next = __ffs(fm) - 1;
       g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
       fm &= fm - 1u;
-#endif
       finish();  // g != 0: there is always a pending super-group here
       // lanes 0..3 store their super-group's two words (zero for a non-candidate super-group of this frame) and count them
       if (my_store) *reinterpret_cast<uint2*>(row) = make_uint2(wl, wh);
       if (COUNT) {
         const bool nz = (wl | wh) != 0u;  // only lanes 0..3 can hold a non-zero word
-#if MSP_C9_COUNT_GLOBAL
         if (nz && my_cnt != nullptr) atomicAdd(my_cnt + (int64_t)fi * p.n_objects, (uint32_t)(__popc(wl) + __popc(wh)));
-#else
-        if (nz && my_slot < (uint32_t)(kC9Slots - 1)) red_smem_add(s_cnt_lane + (uint32_t)fi * (4u * kC9Slots), (uint32_t)(__popc(wl) + __popc(wh)));
-#endif
         uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
         // super-groups that straddle an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
 #pragma unroll 1
@@ -694,12 +655,8 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
             const uint32_t am = __ballot_sync(0xffffffffu, act);
             if (act) {
               const uint32_t grp = __match_any_sync(am, sl);
-#if MSP_C9_COUNT_GLOBAL
               if (lane == __ffs(grp) - 1)
                 atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)T.slot_id[sl] - 1, (uint32_t)__popc(grp));
-#else
-              if (lane == __ffs(grp) - 1) atomicAdd(&s_cnt[fi * kC9Slots + sl], (uint32_t)__popc(grp));
-#endif
             }
             if (bit && sl == kC9SlotOverflow)
               atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
@@ -710,14 +667,6 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
     }
   }
   if (dq != 0u) flush(1u);
-  if (COUNT && !MSP_C9_COUNT_GLOBAL) {
-    __syncthreads();
-    for (int i = tid; i < nf * kC9Slots; i += kC9Threads) {
-      const uint32_t v = s_cnt[i];
-      const uint32_t idv = T.slot_id[i % kC9Slots];
-      if (v != 0u && idv != 0u) atomicAdd(p.counts + (int64_t)(f0 + i / kC9Slots) * p.n_objects + (int)idv - 1, v);
-    }
-  }
 }
 
 // ================================================================================================================
