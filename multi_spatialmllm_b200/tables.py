@@ -102,6 +102,44 @@ def device_scene_from_handler(scene_infos, scene_id: str, device="cuda:0"):
 _JSON_SAFE = frozenset(chr(c) for c in range(0x20, 0x7f)) - {'"', "\\"}
 
 
+class _PinnedPool:
+    """Grow-only pool of pinned host buffers for the table text (200 MB per 200 k-point scene): the device->host copy of a
+    table runs at PCIe speed instead of the ~2 GB/s a fresh pageable allocation gets (page faults), and the buffer goes back
+    to the pool when the Arrow table that wraps it (zero-copy) is released — possibly on a writer thread, hence the lock."""
+
+    def __init__(self):
+        import threading
+        self._free, self._lock = [], threading.Lock()
+
+    def take(self, nbytes: int):
+        import torch
+        with self._lock:
+            fit = [k for k, t in enumerate(self._free) if t.numel() >= nbytes]
+            if fit:
+                k = min(fit, key=lambda i: self._free[i].numel())
+                return self._free.pop(k)            # (list.remove would compare tensors element-wise)
+        return torch.empty((max(int(nbytes * 1.25), 1 << 20),), dtype=torch.uint8, pin_memory=True)
+
+    def give(self, t):
+        with self._lock:
+            if len(self._free) < 24:
+                self._free.append(t)
+
+
+_TEXT_POOL = _PinnedPool()
+
+
+def _to_host_pooled(dev_bytes):
+    """uint8 device tensor -> NumPy view of a pooled pinned buffer; the buffer returns to the pool when the view dies."""
+    import weakref
+    n = int(dev_bytes.numel())
+    pin = _TEXT_POOL.take(n)
+    pin[:n].copy_(dev_bytes)
+    arr = pin[:n].numpy()
+    weakref.finalize(arr, _TEXT_POOL.give, pin)
+    return arr
+
+
 def _check_json_safe(ids):
     for s in ids:
         if not isinstance(s, str) or len(s) > 255 or not set(s) <= _JSON_SAFE:
@@ -166,7 +204,7 @@ def visibility_arrow_table(sc: "engine.DeviceScene", scene_id: str, image_ids):
           "msp_visibility_json_images_write")
     small = total < 2**31
     offs_h = (offs.to(torch.int32) if small else offs).cpu().numpy()
-    text_h = text[:total].cpu().numpy()
+    text_h = _to_host_pooled(text[:total])
     cls = pa.StringArray if small else pa.LargeStringArray
     values = cls.from_buffers(R + n, pa.py_buffer(offs_h), pa.py_buffer(text_h))
     str_t = pa.string() if small else pa.large_string()
