@@ -13,14 +13,15 @@
 //   * the unit of evaluation is a SUPER-GROUP of 64 consecutive points, two per lane, stored as float2 (lo, hi): the whole
 //     float32 projection runs on Blackwell's packed FFMA2 / FADD2 / FMUL2 (fma.rn.f32x2 ...), which take one issue slot
 //     for two points (measured: profiles/r2/ubench_f32x2.txt — half the FMA-pipe rate, but the pipe was only 23 % busy).
-//     Frame coefficients are stored duplicated (c, c) so that they are packed operands straight out of shared memory.
+//     A warp-uniform coefficient is a scalar-broadcast operand of the packed instruction (`R.F32` in SASS): one register.
 //   * group classification runs with lane = FRAME: one pass tests a super-group box against the four half-spaces of 32
 //     frames at once (no ballot, no per-frame head), leaves a 4-bit candidate mask per (warp, frame) in a register, and the
 //     lanes write the all-zero mask words of their non-candidate (frame, super-group)s directly.  The main loop then only
 //     visits frames that have a candidate (ffs over a ballot), in ascending frame order (depth-map locality in L1/L2).
-//   * within a frame the candidate super-groups are software-pipelined by one: the comparison of super-group k runs after
-//     the projection of the next candidate, so that its two depth gathers have a whole projection to land; lanes 0..3
-//     collect the frame's eight mask words and store them once per frame;
+//   * within a frame ALL candidate super-groups of the warp are projected and their depth gathers issued (up to eight
+//     16-bit loads in flight per warp) before the first one is compared: the gather latency is paid once per frame, not
+//     once per super-group (the kernel is bound by that latency at 32 warps x 64 registers per SM, not by bytes); lanes
+//     0..3 collect the frame's eight mask words and store them once per frame;
 //   * uncertain lanes are queued per warp ACROSS frames and the exact float64 path runs on 32 of them at a time, OR-ing
 //     visible bits into the stored words (the validated round-1 "deferred exact" variant, now the only exact path — a
 //     non-standard frame simply queues every lane and becomes the all-float64 kernel at full lane utilisation);
@@ -63,8 +64,8 @@ constexpr int kC9Slots = 16;                                      // local insta
 #define MSP_C9_STRIDED 1       // 1: warp w owns super-groups w, w+8, w+16, w+24 (even work per warp), 0: 4w .. 4w+3
 #endif
 #ifndef MSP_C9_COEF_PER_SG
-#define MSP_C9_COEF_PER_SG 1   // 1: the 12 packed frame coefficients are re-read from shared memory for every super-group (fewer live registers:
-                               //    without it the pending gather state of the pipelined loop spills; measured 0.470 vs 0.535 ms)
+#define MSP_C9_COEF_PER_SG 1   // 1: the 12 frame coefficients are re-read from shared memory for every super-group (fewer live registers
+                               //    next to the up to 16 registers of gather state; 0 measured the same within 0.5 %)
 #endif
 constexpr uint32_t kC9DeferCap = 288;                             // < 32 left over + at most 4 x 64 appended per frame
 #if MSP_C9_STRIDED
@@ -89,19 +90,18 @@ struct __align__(16) CullTilePrep {
 };
 static_assert(sizeof(CullTilePrep) % 16 == 0 && offsetof(CullTilePrep, pt_slot) % 16 == 0, "bulk copy sizes");
 
-struct __align__(16) C9Frame {    // per (tile, frame); 176 bytes = 11 x 16 so that lane = frame LDS.128 accesses are conflict-free
-  float2 a0[4];                   // I0 = sx (fx X + cx Z) as {x, y, z, d'} relative to the tile centre, each value twice (packed operand)
-  float2 a2[4];                   // I1
-  float2 az[4];                   // Z
+struct __align__(16) C9Frame {    // per (tile, frame); 112 bytes = 7 x 16 so that lane = frame LDS.128 accesses are conflict-free
+  float a0[4];                    // I0 = sx (fx X + cx Z) as {x, y, z, d'} relative to the tile centre
+  float a2[4];                    // I1
+  float az[4];                    // Z
   float q1[4];                    // Q1 = dw Z - I0 (classification only)
   float q3[4];                    // Q3 = dh Z - I1
-  float2 ct1, hct0, Bz;           // pixel guard band dt = ct1 rcp(Z) + ct0 as (ct1, 0.5 - ct0); depth-form bound; duplicated
-  float B, B2;                    // common bound of the four in-image forms, and twice that
+  float ct1, hct0, Bz, B;         // pixel guard band dt = ct1 rcp(Z) + ct0 as (ct1, 0.5 - ct0); depth-form bound; bound of the in-image forms
   unsigned long long dm_biased;   // depth map byte address - 2 * 0x4B000000 (gather index = as_uint(di + 2^23))
   int std_frame;                  // bottom row of w2c is exactly [0,0,0,1]
   uint32_t pad;
 };
-static_assert(sizeof(C9Frame) == 176, "C9Frame layout");
+static_assert(sizeof(C9Frame) == 112, "C9Frame layout");
 
 // ---- packed float32x2 arithmetic (one issue slot for two IEEE single operations; FFMA2 / FADD2 / FMUL2 in SASS) ----------
 typedef unsigned long long f32x2;
@@ -110,6 +110,9 @@ __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
   asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
+// (c, c): ptxas recognises the repeated register and emits the packed instruction's scalar-broadcast operand form (`R6.F32` in SASS),
+// so a warp-uniform coefficient costs ONE register, not a duplicated pair
+__device__ __forceinline__ f32x2 bc2(float c) { return pk2(c, c); }
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 d;
@@ -134,6 +137,11 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ f32x2 lds64(uint32_t addr) {
   f32x2 v;
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void lds128(uint32_t addr, f32x2& a, f32x2& b) {
@@ -361,17 +369,16 @@ __device__ __forceinline__ void c9_frame_consts(const double* __restrict__ w, co
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    c.a0[k] = make_float2(co[0][k], co[0][k]);
-    c.a2[k] = make_float2(co[2][k], co[2][k]);
-    c.az[k] = make_float2(co[4][k], co[4][k]);
+    c.a0[k] = co[0][k];
+    c.a2[k] = co[2][k];
+    c.az[k] = co[4][k];
     c.q1[k] = co[1][k];
     c.q3[k] = co[3][k];
   }
-  c.ct1 = make_float2(ct1, ct1);
-  c.hct0 = make_float2(0.5f - ct0, 0.5f - ct0);
-  c.Bz = make_float2(Bz, Bz);
+  c.ct1 = ct1;
+  c.hct0 = 0.5f - ct0;
+  c.Bz = Bz;
   c.B = Bf32;
-  c.B2 = Bf32 + Bf32;
   c.dm_biased = (unsigned long long)depth_map - 2ull * 0x4B000000ull;
   c.pad = 0u;
 }
@@ -379,11 +386,8 @@ __device__ __forceinline__ void c9_frame_consts(const double* __restrict__ w, co
 struct Cull9Params {
   CullParams p;               // the caller's arrays (msp_cull.cuh)
   const CullTilePrep* prep;   // one per tile (k_cull_prepare)
-  f32x2 nfdw2, nfdh2;         // (-dw,-dw), (-dh,-dh)
-  f32x2 fdw2;                 // (dw, dw)
-  f32x2 magic2;               // (1.5 * 2^23) x 2
-  f32x2 two23_2, ntwo23_2;    // (2^23) x 2, (-2^23) x 2
-  f32x2 fscale2, c36_2;       // depth scale, 3.6e-7
+  float nfdw, nfdh, fdw;      // -depth_w, -depth_h, depth_w as float32 (exact)
+  float fscale;               // float32 rounding of depth_scale (its error is inside the 6u d guard)
   float xclip, yclip;         // dw - 1 + 2^23, dh - 1
 };
 
@@ -446,20 +450,19 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
     uint32_t gm = 0u;
     if (fi < nf) {
       const C9Frame& c = s_c[fi];
-      const float4 a0l = *reinterpret_cast<const float4*>(&c.a0[0]), a0h = *reinterpret_cast<const float4*>(&c.a0[2]);
-      const float4 a2l = *reinterpret_cast<const float4*>(&c.a2[0]), a2h = *reinterpret_cast<const float4*>(&c.a2[2]);
+      const float4 a0 = *reinterpret_cast<const float4*>(c.a0), a2 = *reinterpret_cast<const float4*>(c.a2);
       const float4 q1 = *reinterpret_cast<const float4*>(c.q1), q3 = *reinterpret_cast<const float4*>(c.q3);
       const float nB = -c.B;
 #pragma unroll
       for (int k = 0; k < kC9SgPerWarp; ++k) {
         const float4 bc = T.box[MSP_C9_SG(warp, k)][0], bh = T.box[MSP_C9_SG(warp, k)][1];
         // form value at the box centre + |a| . half size (rounded up) >= -B for all four forms; NaN (empty box, NaN pose) -> false
-        const float v0 = fmaf(a0l.x, bc.x, fmaf(a0l.z, bc.y, fmaf(a0h.x, bc.z, a0h.z)));
-        const float r0 = __fmaf_ru(fabsf(a0l.x), bh.x, __fmaf_ru(fabsf(a0l.z), bh.y, __fmul_ru(fabsf(a0h.x), bh.z)));
+        const float v0 = fmaf(a0.x, bc.x, fmaf(a0.y, bc.y, fmaf(a0.z, bc.z, a0.w)));
+        const float r0 = __fmaf_ru(fabsf(a0.x), bh.x, __fmaf_ru(fabsf(a0.y), bh.y, __fmul_ru(fabsf(a0.z), bh.z)));
         const float v1 = fmaf(q1.x, bc.x, fmaf(q1.y, bc.y, fmaf(q1.z, bc.z, q1.w)));
         const float r1 = __fmaf_ru(fabsf(q1.x), bh.x, __fmaf_ru(fabsf(q1.y), bh.y, __fmul_ru(fabsf(q1.z), bh.z)));
-        const float v2 = fmaf(a2l.x, bc.x, fmaf(a2l.z, bc.y, fmaf(a2h.x, bc.z, a2h.z)));
-        const float r2 = __fmaf_ru(fabsf(a2l.x), bh.x, __fmaf_ru(fabsf(a2l.z), bh.y, __fmul_ru(fabsf(a2h.x), bh.z)));
+        const float v2 = fmaf(a2.x, bc.x, fmaf(a2.y, bc.y, fmaf(a2.z, bc.z, a2.w)));
+        const float r2 = __fmaf_ru(fabsf(a2.x), bh.x, __fmaf_ru(fabsf(a2.y), bh.y, __fmul_ru(fabsf(a2.z), bh.z)));
         const float v3 = fmaf(q3.x, bc.x, fmaf(q3.y, bc.y, fmaf(q3.z, bc.z, q3.w)));
         const float r3 = __fmaf_ru(fabsf(q3.x), bh.x, __fmaf_ru(fabsf(q3.y), bh.y, __fmul_ru(fabsf(q3.z), bh.z)));
         const bool cand = (__fadd_ru(v0, r0) >= nB) && (__fadd_ru(v1, r1) >= nB) && (__fadd_ru(v2, r2) >= nB) && (__fadd_ru(v3, r3) >= nB);
@@ -512,10 +515,11 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
     __syncwarp();  // the queue may be refilled
   };
 
-  // ---- B + C: frames with candidates, ascending.  Within a frame the candidate super-groups are software-pipelined by one:
-  // while the two depth gathers of super-group k are in flight the warp projects the next candidate, and only then compares k;
-  // the last one of the frame is compared at the frame's end (nothing is carried over the loop's back-edge: ptxas then shares
-  // the gather's scoreboard with the loop head's FLO / SHFL and waits there, profiles/r2/k1_tuning.md).
+  // ---- B + C: frames with candidates, ascending.  Per frame the warp projects ALL its candidate super-groups and issues
+  // their depth gathers (up to eight loads in flight per warp), looks the next candidate frame up, and only then compares
+  // them: the wait is paid once per frame.  Nothing is pending at the loop's back-edge, and the only wait is for "all gathers
+  // of this frame": ptxas puts every gather on ONE scoreboard, so a deeper pipeline (a second frame or super-group in flight
+  // while the first is compared) waits for the younger loads as well (profiles/r2/k1_tuning.md, v10 / v17 / v18).
   // A lane that does not gather (outside the image, or uncertain) reads pixel 0 of the map (always mapped, L1-resident) and
   // carries z = +inf ("certainly not visible") or z = NaN ("uncertain"): t = z - d is then +inf / NaN for any d, so
   // `t < -mz` is false and the uncertainty test !(|t| > mz) is false / true as required — the comparison needs no predicates.
@@ -524,128 +528,25 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
   const bool my_store = (lane < kC9SgPerWarp) && ((okm >> lane) & 1u);
   uint32_t my_slot = kC9SlotNone;  // COUNT: sg_slot of super-group k = lane (lanes 0..3)
   if (COUNT && lane < kC9SgPerWarp) my_slot = T.sg_slot[my_sg];
-  // lanes 0..3: counts + (instance id - 1) of the lane's super-group when all its points share one id, else NULL
-  uint32_t* my_cnt = nullptr;
-  if (COUNT && my_slot < (uint32_t)(kC9Slots - 1)) my_cnt = p.counts + (int64_t)f0 * p.n_objects + (int)T.slot_id[my_slot] - 1;
-#pragma unroll 1
-  for (int r = 0; r < kC9Rounds; ++r) {
-    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
-    int fl_next = __ffs(fm) - 1;                                              // -1: no candidate frame in this round
-    uint32_t g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
-    fm &= fm - 1u;
-#pragma unroll 1
-    while (fl_next >= 0) {
-      const int fl = fl_next;
-      const uint32_t g = g_next;
-      const int fi = 32 * r + fl;
-      const uint32_t s_cf = smem_u32(&s_c[fi]);
-#if !MSP_C9_COEF_PER_SG
-      f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
-      lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
-      lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
-      lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
-#endif
-      f32x2 ct1_2, hct0_2, Bz2, BB;
-      lds128(s_cf + 128, ct1_2, hct0_2);
-      lds128(s_cf + 144, Bz2, BB);
-      float Bq, B2q;
-      upk2(BB, Bq, B2q);
-      const float nB = -Bq;
-      const unsigned long long dm = lds64(s_cf + 160);
-      uint32_t* row = mask0 + (int64_t)fi * p.mask_stride + 2 * my_sg;  // lanes 0..3: this frame's two words of super-group k = lane
-      asm volatile("" : "+l"(row));
-      uint32_t wl = 0u, wh = 0u;  // lanes 0..3: those two words
-      int pk = -1;                // pending super-group (its gathers are in flight), -1 = none
-      f32x2 pz = 0ull;
-      uint32_t prl = 0u, prh = 0u;
-      auto finish = [&]() {
-        // depth: d^ = fl(float(raw) * 0.001f); visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^)
-        const f32x2 d = mul2(add2(pk2(__uint_as_float(0x4B000000u | prl), __uint_as_float(0x4B000000u | prh)), q.ntwo23_2), q.fscale2);
-        const f32x2 mz = fma2(q.c36_2, d, Bz2);
-        const f32x2 t = sub2(pz, d);
-        float tl, th, mzl, mzh;
-        upk2(t, tl, th), upk2(mz, mzl, mzh);
-        const bool visl = tl < -mzl, vish = th < -mzh;
-        const bool uncl = !(fabsf(tl) > mzl), unch = !(fabsf(th) > mzh);
-        const uint32_t bvl = __ballot_sync(0xffffffffu, visl), bvh = __ballot_sync(0xffffffffu, vish);
-        const uint32_t bu = __ballot_sync(0xffffffffu, uncl | unch);
-        if (lane == pk) wl = bvl, wh = bvh;
-        if (bu != 0u) {  // rare, warp-uniform: queue the uncertain lanes (lo half first); flushed after this frame's words are stored
-          const uint32_t bul = __ballot_sync(0xffffffffu, uncl), buh = __ballot_sync(0xffffffffu, unch);
-          const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)pk << 6) | (uint32_t)lane;
-          if (uncl) s_dq[warp][dq + __popc(bul & lt)] = (uint16_t)code;
-          dq += __popc(bul);
-          if (unch) s_dq[warp][dq + __popc(buh & lt)] = (uint16_t)(code | 32u);
-          dq += __popc(buh);
-        }
-      };
-#pragma unroll
-      for (int k = 0; k < kC9SgPerWarp; ++k) {
-        if (!((g >> k) & 1u)) continue;  // warp-uniform
-        const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
-        const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
-#if MSP_C9_COEF_PER_SG
-        f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw;
-        lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
-        lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
-        lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
-#endif
-        const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
-        const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
-        const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
-        const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);  // I0 - dw Z = -Q1 (same rounding as fl(dw Z - I0))
-        const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
-        float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
-        upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
-        // m = min(I0, Q1, I1, Q3); NaN only for empty / non-finite slots: never visible, never queued
-        const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
-        const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
-        const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));  // s = -1/Z (max relative error 2^-23, covered by ct0/ct1)
-        // rint(t) with t = I0 / Z: (-t + 1.5 * 2^23) is an exact integer shift for |t| < 2^22; lanes beyond are never `go`
-        const f32x2 nixm = fma2(I0, s, q.magic2);
-        const f32x2 ix = sub2(q.magic2, nixm);  // = rint(tx), exact
-        const f32x2 fx = fma2(I0, s, ix);       // rint(tx) - tx
-        const f32x2 niym = fma2(I1, s, q.magic2);
-        const f32x2 iy = sub2(q.magic2, niym);
-        const f32x2 fy = fma2(I1, s, iy);
-        const f32x2 thr = fma2(ct1_2, s, hct0_2);  // 1/2 - ct0 - ct1 / Z
-        float fxl, fxh, fyl, fyh, thl, thh;
-        upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
-        // the reference rounds to the same depth pixel, and the point is certainly inside the image in front of the camera
-        const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
-        const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
-        // gather index: di + 2^23 as an exact float, i.e. the bit pattern 0x4B000000 + di (dm is pre-biased by that constant)
-        const f32x2 ixb = add2(ix, q.two23_2);
-        float ixl, ixh, iyl, iyh;
-        upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
-        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
-        float dbl, dbh;
-        upk2(dbits, dbl, dbh);
-        const uint32_t bitl = gol ? __float_as_uint(dbl) : 0x4B000000u, bith = goh ? __float_as_uint(dbh) : 0x4B000000u;
-        const f32x2 zsel = pk2(gol ? Zl : ((ml >= nB) ? qnan : finf), goh ? Zh : ((mh >= nB) ? qnan : finf));
-        if (pk >= 0) finish();  // the previous candidate's gathers have had this whole projection to land
-        prl = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bitl));
-        prh = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bith));
-        pz = zsel;
-        pk = k;
-      }
-      // the frame's last gathers are in flight: look the next candidate frame up now
-      fl_next = __ffs(fm) - 1;
-      g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
-      fm &= fm - 1u;
-      finish();  // g != 0: there is always a pending super-group here
-      // lanes 0..3 store their super-group's two words (zero for a non-candidate super-group of this frame) and count them
-      if (my_store) *reinterpret_cast<uint2*>(row) = make_uint2(wl, wh);
-      if (COUNT) {
-        const bool nz = (wl | wh) != 0u;  // only lanes 0..3 can hold a non-zero word
-        if (nz && my_cnt != nullptr) atomicAdd(my_cnt + (int64_t)fi * p.n_objects, (uint32_t)(__popc(wl) + __popc(wh)));
-        uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
+  // lanes 0..3: instance id - 1 of the lane's super-group when all its points share one id, else -1
+  int my_obj = -1;
+  if (COUNT && my_slot < (uint32_t)(kC9Slots - 1)) my_obj = (int)T.slot_id[my_slot] - 1;
+  const bool any_mixed = COUNT && __any_sync(0xffffffffu, my_slot == kC9SlotMixed);
+  // lanes 0..3 store their super-group's two words of frame fi (zero for a non-candidate super-group) and count them
+  auto store_frame = [&](int fi, uint32_t pwl, uint32_t pwh) {
+    const int64_t f = f0 + fi;
+    if (my_store) *reinterpret_cast<uint2*>(p.mask + f * p.mask_stride + word0 + 2 * my_sg) = make_uint2(pwl, pwh);
+    if (COUNT) {
+      const bool nz = (pwl | pwh) != 0u;  // only lanes 0..3 can hold a non-zero word
+      if (nz && my_obj >= 0) atomicAdd(p.counts + f * p.n_objects + my_obj, (uint32_t)(__popc(pwl) + __popc(pwh)));
+      if (any_mixed) {
         // super-groups that straddle an object boundary (rare on mesh-ordered clouds): aggregate by slot within the warp
+        uint32_t mg = __ballot_sync(0xffffffffu, nz && my_slot == kC9SlotMixed);
 #pragma unroll 1
         while (mg != 0u) {
           const int k = __ffs(mg) - 1;
           mg &= mg - 1u;
-          const uint32_t wvl = __shfl_sync(0xffffffffu, wl, k), wvh = __shfl_sync(0xffffffffu, wh, k);
+          const uint32_t wvl = __shfl_sync(0xffffffffu, pwl, k), wvh = __shfl_sync(0xffffffffu, pwh, k);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int idx = MSP_C9_SG(warp, k) * 64 + 32 * h + lane;
@@ -655,15 +556,109 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
             const uint32_t am = __ballot_sync(0xffffffffu, act);
             if (act) {
               const uint32_t grp = __match_any_sync(am, sl);
-              if (lane == __ffs(grp) - 1)
-                atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)T.slot_id[sl] - 1, (uint32_t)__popc(grp));
+              if (lane == __ffs(grp) - 1) atomicAdd(p.counts + f * p.n_objects + (int)T.slot_id[sl] - 1, (uint32_t)__popc(grp));
             }
-            if (bit && sl == kC9SlotOverflow)
-              atomicAdd(p.counts + (int64_t)(f0 + fi) * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
+            if (bit && sl == kC9SlotOverflow) atomicAdd(p.counts + f * p.n_objects + (int)__ldg(p.inst + base + idx) - 1, 1u);
           }
         }
       }
-      if (dq >= 32u) flush(32u);  // after this frame's words have been stored
+    }
+    if (dq >= 32u) flush(32u);  // every queued point belongs to a frame whose words have been stored
+  };
+#pragma unroll 1
+  for (int r = 0; r < kC9Rounds; ++r) {
+    uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
+    int fl_next = __ffs(fm) - 1;                                              // -1: no candidate frame in this round
+    uint32_t g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
+    fm &= fm - 1u;
+#pragma unroll 1
+    while (fl_next >= 0) {
+      const uint32_t g = g_next;
+      const int fi = 32 * r + fl_next;
+      const uint32_t s_cf = smem_u32(&s_c[fi]);
+#if !MSP_C9_COEF_PER_SG
+      const float4 a0 = lds_f4(s_cf + 0), a2 = lds_f4(s_cf + 16), az = lds_f4(s_cf + 32);
+#endif
+      const float4 sc4 = lds_f4(s_cf + 80);  // ct1, 1/2 - ct0, B_Z, B
+      const f32x2 ct1_2 = bc2(sc4.x), hct0_2 = bc2(sc4.y);
+      const float B2q = sc4.w + sc4.w, nB = -sc4.w;
+      const unsigned long long dm = lds64(s_cf + 96);
+      // the frame's candidate super-groups in flight: float32 z of the two points of a lane, the two gathered raw depths
+      f32x2 bz[kC9SgPerWarp];
+      uint32_t brl[kC9SgPerWarp], brh[kC9SgPerWarp];  // statically indexed: registers
+#pragma unroll
+      for (int k = 0; k < kC9SgPerWarp; ++k) {
+        if (!((g >> k) & 1u)) continue;  // warp-uniform
+        const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
+        const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
+#if MSP_C9_COEF_PER_SG
+        const float4 a0 = lds_f4(s_cf + 0), a2 = lds_f4(s_cf + 16), az = lds_f4(s_cf + 32);
+#endif
+        const f32x2 I0 = fma2(bc2(a0.x), xx, fma2(bc2(a0.y), yy, fma2(bc2(a0.z), zz, bc2(a0.w))));
+        const f32x2 I1 = fma2(bc2(a2.x), xx, fma2(bc2(a2.y), yy, fma2(bc2(a2.z), zz, bc2(a2.w))));
+        const f32x2 Zp = fma2(bc2(az.x), xx, fma2(bc2(az.y), yy, fma2(bc2(az.z), zz, bc2(az.w))));
+        const f32x2 nQ1 = fma2(bc2(q.nfdw), Zp, I0);  // I0 - dw Z = -Q1 (same rounding as fl(dw Z - I0))
+        const f32x2 nQ3 = fma2(bc2(q.nfdh), Zp, I1);
+        float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
+        upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
+        // m = min(I0, Q1, I1, Q3); NaN only for empty / non-finite slots: never visible, never queued
+        const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
+        const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
+        const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));  // s = -1/Z (max relative error 2^-23, covered by ct0/ct1)
+        // rint(t) with t = I0 / Z: (-t + 1.5 * 2^23) is an exact integer shift for |t| < 2^22; lanes beyond are never `go`
+        const f32x2 nixm = fma2(I0, s, bc2(12582912.0f));
+        const f32x2 ix = sub2(bc2(12582912.0f), nixm);  // = rint(tx), exact
+        const f32x2 fx = fma2(I0, s, ix);       // rint(tx) - tx
+        const f32x2 niym = fma2(I1, s, bc2(12582912.0f));
+        const f32x2 iy = sub2(bc2(12582912.0f), niym);
+        const f32x2 fy = fma2(I1, s, iy);
+        const f32x2 thr = fma2(ct1_2, s, hct0_2);  // 1/2 - ct0 - ct1 / Z
+        float fxl, fxh, fyl, fyh, thl, thh;
+        upk2(fx, fxl, fxh), upk2(fy, fyl, fyh), upk2(thr, thl, thh);
+        // the reference rounds to the same depth pixel, and the point is certainly inside the image in front of the camera
+        const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
+        const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
+        // gather index: di + 2^23 as an exact float, i.e. the bit pattern 0x4B000000 + di (dm is pre-biased by that constant)
+        const f32x2 ixb = add2(ix, bc2(8388608.0f));
+        float ixl, ixh, iyl, iyh;
+        upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
+        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), bc2(q.fdw), pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
+        float dbl, dbh;
+        upk2(dbits, dbl, dbh);
+        const uint32_t bitl = gol ? __float_as_uint(dbl) : 0x4B000000u, bith = goh ? __float_as_uint(dbh) : 0x4B000000u;
+        bz[k] = pk2(gol ? Zl : ((ml >= nB) ? qnan : finf), goh ? Zh : ((mh >= nB) ? qnan : finf));
+        brl[k] = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bitl));
+        brh[k] = ldg_u16_nc(reinterpret_cast<const uint16_t*>(dm + 2ull * bith));
+      }
+      // the frame's gathers are in flight: look the next candidate frame up now
+      fl_next = __ffs(fm) - 1;
+      g_next = __shfl_sync(0xffffffffu, gmr[r], fl_next & 31);
+      fm &= fm - 1u;
+      uint32_t wl = 0u, wh = 0u;
+#pragma unroll
+      for (int k = 0; k < kC9SgPerWarp; ++k) {
+        if (!((g >> k) & 1u)) continue;
+        // depth: d^ = fl(float(raw) * 0.001f); visible iff z < d is certain when Z^ < d^ - (B_Z + 6u d^)
+        const f32x2 d = mul2(add2(pk2(__uint_as_float(0x4B000000u | brl[k]), __uint_as_float(0x4B000000u | brh[k])), bc2(-8388608.0f)), bc2(q.fscale));
+        const f32x2 mz = fma2(bc2(3.6e-7f), d, bc2(sc4.z));
+        const f32x2 t = sub2(bz[k], d);
+        float tl, th, mzl, mzh;
+        upk2(t, tl, th), upk2(mz, mzl, mzh);
+        const bool visl = tl < -mzl, vish = th < -mzh;
+        const bool uncl = !(fabsf(tl) > mzl), unch = !(fabsf(th) > mzh);
+        const uint32_t bvl = __ballot_sync(0xffffffffu, visl), bvh = __ballot_sync(0xffffffffu, vish);
+        const uint32_t bu = __ballot_sync(0xffffffffu, uncl | unch);
+        if (lane == k) wl = bvl, wh = bvh;
+        if (bu != 0u) {  // rare, warp-uniform: queue the uncertain lanes (lo half first); worked off once the frame's words are stored
+          const uint32_t bul = __ballot_sync(0xffffffffu, uncl), buh = __ballot_sync(0xffffffffu, unch);
+          const uint32_t code = ((uint32_t)fi << 8) | ((uint32_t)k << 6) | (uint32_t)lane;
+          if (uncl) s_dq[warp][dq + __popc(bul & lt)] = (uint16_t)code;
+          dq += __popc(bul);
+          if (unch) s_dq[warp][dq + __popc(buh & lt)] = (uint16_t)(code | 32u);
+          dq += __popc(buh);
+        }
+      }
+      store_frame(fi, wl, wh);
     }
   }
   if (dq != 0u) flush(1u);
@@ -678,14 +673,14 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_frame_cull9(co
 // original coordinates from global memory, z = row 2 of w2c . [x y z 1] in the reference's float64 operation order (certain
 // pixel) or the whole exact projection (uncertain), then one atomicMin on the ordered float bits.
 // ================================================================================================================
-static_assert(kC9Frames <= 32, "k_zbuf_cull9 packs the frame index of a queued point into 5 bits");
+constexpr int kZ9Frames = 32, kZ9Rounds = 1;  // frames per CTA of k_zbuf_cull9: it packs the frame index of a queued point into 5 bits
 constexpr uint32_t kZ9NoPixel = 0x7ffffu;  // 19-bit pixel field: "uncertain, run the exact projection" (needs depth_w * depth_h < 2^19 - 1)
 
 template <int DT>
 __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_zbuf_cull9(const Cull9Params q) {
   extern __shared__ __align__(128) unsigned char s_raw[];  // CullTilePrep without the instance part
-  __shared__ __align__(16) C9Frame s_c[kC9Frames];
-  __shared__ __align__(16) double s_wz[kC9Frames][4];       // row 2 of every frame's w2c (the z form, float64)
+  __shared__ __align__(16) C9Frame s_c[kZ9Frames];
+  __shared__ __align__(16) double s_wz[kZ9Frames][4];       // row 2 of every frame's w2c (the z form, float64)
   __shared__ uint32_t s_zq[kC9Warps][96];                   // pixel << 13 | frame in chunk << 8 | k << 6 | half << 5 | lane
   __shared__ __align__(8) uint64_t s_bar;
   const CullParams& p = q.p;
@@ -694,8 +689,8 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_zbuf_cull9(con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = (int64_t)blockIdx.x * kC9TilePoints;
   const int cnt = (int)min((int64_t)kC9TilePoints, p.n - base);
-  const int f0 = blockIdx.y * kC9Frames;
-  const int nf = min(kC9Frames, p.F - f0);
+  const int f0 = blockIdx.y * kZ9Frames;
+  const int nf = min(kZ9Frames, p.F - f0);
   const CullTilePrep* gprep = q.prep + blockIdx.x;
 
   if (tid == 0) {
@@ -724,26 +719,25 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_zbuf_cull9(con
   constexpr uint32_t kSgStride = (uint32_t)(MSP_C9_SG(0, 1) - MSP_C9_SG(0, 0)) * 768u;
 
   // ---- A: classification, lane = frame (as in K1)
-  uint32_t gmr[kC9Rounds];
+  uint32_t gmr[kZ9Rounds];
 #pragma unroll
-  for (int r = 0; r < kC9Rounds; ++r) {
+  for (int r = 0; r < kZ9Rounds; ++r) {
     const int fi = 32 * r + lane;
     uint32_t gm = 0u;
     if (fi < nf) {
       const C9Frame& c = s_c[fi];
-      const float4 a0l = *reinterpret_cast<const float4*>(&c.a0[0]), a0h = *reinterpret_cast<const float4*>(&c.a0[2]);
-      const float4 a2l = *reinterpret_cast<const float4*>(&c.a2[0]), a2h = *reinterpret_cast<const float4*>(&c.a2[2]);
+      const float4 a0 = *reinterpret_cast<const float4*>(c.a0), a2 = *reinterpret_cast<const float4*>(c.a2);
       const float4 q1 = *reinterpret_cast<const float4*>(c.q1), q3 = *reinterpret_cast<const float4*>(c.q3);
       const float nB = -c.B;
 #pragma unroll
       for (int k = 0; k < kC9SgPerWarp; ++k) {
         const float4 bc = T.box[MSP_C9_SG(warp, k)][0], bh = T.box[MSP_C9_SG(warp, k)][1];
-        const float v0 = fmaf(a0l.x, bc.x, fmaf(a0l.z, bc.y, fmaf(a0h.x, bc.z, a0h.z)));
-        const float r0 = __fmaf_ru(fabsf(a0l.x), bh.x, __fmaf_ru(fabsf(a0l.z), bh.y, __fmul_ru(fabsf(a0h.x), bh.z)));
+        const float v0 = fmaf(a0.x, bc.x, fmaf(a0.y, bc.y, fmaf(a0.z, bc.z, a0.w)));
+        const float r0 = __fmaf_ru(fabsf(a0.x), bh.x, __fmaf_ru(fabsf(a0.y), bh.y, __fmul_ru(fabsf(a0.z), bh.z)));
         const float v1 = fmaf(q1.x, bc.x, fmaf(q1.y, bc.y, fmaf(q1.z, bc.z, q1.w)));
         const float r1 = __fmaf_ru(fabsf(q1.x), bh.x, __fmaf_ru(fabsf(q1.y), bh.y, __fmul_ru(fabsf(q1.z), bh.z)));
-        const float v2 = fmaf(a2l.x, bc.x, fmaf(a2l.z, bc.y, fmaf(a2h.x, bc.z, a2h.z)));
-        const float r2 = __fmaf_ru(fabsf(a2l.x), bh.x, __fmaf_ru(fabsf(a2l.z), bh.y, __fmul_ru(fabsf(a2h.x), bh.z)));
+        const float v2 = fmaf(a2.x, bc.x, fmaf(a2.y, bc.y, fmaf(a2.z, bc.z, a2.w)));
+        const float r2 = __fmaf_ru(fabsf(a2.x), bh.x, __fmaf_ru(fabsf(a2.y), bh.y, __fmul_ru(fabsf(a2.z), bh.z)));
         const float v3 = fmaf(q3.x, bc.x, fmaf(q3.y, bc.y, fmaf(q3.z, bc.z, q3.w)));
         const float r3 = __fmaf_ru(fabsf(q3.x), bh.x, __fmaf_ru(fabsf(q3.y), bh.y, __fmul_ru(fabsf(q3.z), bh.z)));
         const bool cand = (__fadd_ru(v0, r0) >= nB) && (__fadd_ru(v1, r1) >= nB) && (__fadd_ru(v2, r2) >= nB) && (__fadd_ru(v3, r3) >= nB);
@@ -783,7 +777,7 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_zbuf_cull9(con
   };
 
 #pragma unroll 1
-  for (int r = 0; r < kC9Rounds; ++r) {
+  for (int r = 0; r < kZ9Rounds; ++r) {
     uint32_t fm = __ballot_sync(0xffffffffu, gmr[r] != 0u);
 #pragma unroll 1
     while (fm != 0u) {
@@ -792,36 +786,30 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_zbuf_cull9(con
       uint32_t g = __shfl_sync(0xffffffffu, gmr[r], fl);
       const int fi = 32 * r + fl;
       const uint32_t s_cf = smem_u32(&s_c[fi]);
-      f32x2 a0x, a0y, a0z, a0w, a2x, a2y, a2z, a2w, azx, azy, azz, azw, ct1_2, hct0_2, Bz2, BB;
-      lds128(s_cf + 0, a0x, a0y), lds128(s_cf + 16, a0z, a0w);
-      lds128(s_cf + 32, a2x, a2y), lds128(s_cf + 48, a2z, a2w);
-      lds128(s_cf + 64, azx, azy), lds128(s_cf + 80, azz, azw);
-      lds128(s_cf + 128, ct1_2, hct0_2);
-      lds128(s_cf + 144, Bz2, BB);
-      float Bq, B2q;
-      upk2(BB, Bq, B2q);
-      const float nB = -Bq;
+      const float4 a0 = lds_f4(s_cf + 0), a2 = lds_f4(s_cf + 16), az = lds_f4(s_cf + 32), sc4 = lds_f4(s_cf + 80);
+      const f32x2 ct1_2 = bc2(sc4.x), hct0_2 = bc2(sc4.y);
+      const float B2q = sc4.w + sc4.w, nB = -sc4.w;
 #pragma unroll 1
       while (g != 0u) {
         const int k = __ffs(g) - 1;
         g &= g - 1u;
         const uint32_t pa = s_lane + kSgStride * (uint32_t)k;
         const f32x2 xx = lds64(pa), yy = lds64(pa + 256u), zz = lds64(pa + 512u);
-        const f32x2 I0 = fma2(a0x, xx, fma2(a0y, yy, fma2(a0z, zz, a0w)));
-        const f32x2 I1 = fma2(a2x, xx, fma2(a2y, yy, fma2(a2z, zz, a2w)));
-        const f32x2 Zp = fma2(azx, xx, fma2(azy, yy, fma2(azz, zz, azw)));
-        const f32x2 nQ1 = fma2(q.nfdw2, Zp, I0);
-        const f32x2 nQ3 = fma2(q.nfdh2, Zp, I1);
+        const f32x2 I0 = fma2(bc2(a0.x), xx, fma2(bc2(a0.y), yy, fma2(bc2(a0.z), zz, bc2(a0.w))));
+        const f32x2 I1 = fma2(bc2(a2.x), xx, fma2(bc2(a2.y), yy, fma2(bc2(a2.z), zz, bc2(a2.w))));
+        const f32x2 Zp = fma2(bc2(az.x), xx, fma2(bc2(az.y), yy, fma2(bc2(az.z), zz, bc2(az.w))));
+        const f32x2 nQ1 = fma2(bc2(q.nfdw), Zp, I0);
+        const f32x2 nQ3 = fma2(bc2(q.nfdh), Zp, I1);
         float I0l, I0h, I1l, I1h, Zl, Zh, nq1l, nq1h, nq3l, nq3h;
         upk2(I0, I0l, I0h), upk2(I1, I1l, I1h), upk2(Zp, Zl, Zh), upk2(nQ1, nq1l, nq1h), upk2(nQ3, nq3l, nq3h);
         const float ml = fminf(fminf(I0l, I1l), -fmaxf(nq1l, nq3l));
         const float mh = fminf(fminf(I0h, I1h), -fmaxf(nq1h, nq3h));
         const f32x2 s = pk2(rcp_approx(-Zl), rcp_approx(-Zh));
-        const f32x2 nixm = fma2(I0, s, q.magic2);
-        const f32x2 ix = sub2(q.magic2, nixm);
+        const f32x2 nixm = fma2(I0, s, bc2(12582912.0f));
+        const f32x2 ix = sub2(bc2(12582912.0f), nixm);
         const f32x2 fx = fma2(I0, s, ix);
-        const f32x2 niym = fma2(I1, s, q.magic2);
-        const f32x2 iy = sub2(q.magic2, niym);
+        const f32x2 niym = fma2(I1, s, bc2(12582912.0f));
+        const f32x2 iy = sub2(bc2(12582912.0f), niym);
         const f32x2 fy = fma2(I1, s, iy);
         const f32x2 thr = fma2(ct1_2, s, hct0_2);
         float fxl, fxh, fyl, fyh, thl, thh;
@@ -829,10 +817,10 @@ __global__ void __launch_bounds__(kC9Threads, MSP_C9_MINBLOCKS) k_zbuf_cull9(con
         const bool gol = (fmaxf(fabsf(fxl), fabsf(fyl)) <= thl) && (ml >= B2q);
         const bool goh = (fmaxf(fabsf(fxh), fabsf(fyh)) <= thh) && (mh >= B2q);
         const bool uncl = !gol && (ml >= nB), unch = !goh && (mh >= nB);
-        const f32x2 ixb = add2(ix, q.two23_2);
+        const f32x2 ixb = add2(ix, bc2(8388608.0f));
         float ixl, ixh, iyl, iyh;
         upk2(ixb, ixl, ixh), upk2(iy, iyl, iyh);
-        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), q.fdw2, pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
+        const f32x2 dbits = fma2(pk2(fminf(iyl, q.yclip), fminf(iyh, q.yclip)), bc2(q.fdw), pk2(fminf(ixl, q.xclip), fminf(ixh, q.xclip)));
         float dbl, dbh;
         upk2(dbits, dbl, dbh);
         // queue every lane that may land on a pixel: certain ones with the pixel, uncertain ones with the "no pixel" mark

@@ -826,15 +826,8 @@ static int launch_cull9(const FrameLoopParams& p, int dt, cudaStream_t s) {
   c.stats = g_cull_stats;
   c.inst = p.inst, c.counts = p.counts, c.n_objects = p.n_objects;
   q.prep = prep;
-  const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h, fscale = (float)p.g.depth_scale;
-  auto dup = [](float v) {
-    uint32_t b;
-    memcpy(&b, &v, 4);
-    return (unsigned long long)b | ((unsigned long long)b << 32);
-  };
-  q.nfdw2 = dup(-fdw), q.nfdh2 = dup(-fdh), q.fdw2 = dup(fdw);
-  q.magic2 = dup(12582912.0f), q.two23_2 = dup(8388608.0f), q.ntwo23_2 = dup(-8388608.0f);
-  q.fscale2 = dup(fscale), q.c36_2 = dup(3.6e-7f);
+  const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h;
+  q.nfdw = -fdw, q.nfdh = -fdh, q.fdw = fdw, q.fscale = (float)p.g.depth_scale;
   q.xclip = (fdw - 1.0f) + 8388608.0f, q.yclip = fdh - 1.0f;
   int rc = MSP_OK;
 #define MSP_C9_LAUNCH(DT, CNT)                                                                                      \
@@ -861,7 +854,7 @@ static int launch_cull9(const FrameLoopParams& p, int dt, cudaStream_t s) {
 // K2 second generation (k_zbuf_cull9): prepare pass + packed projection + batched float64 splat.
 static int launch_zbuf9(const FrameLoopParams& p, int dt, cudaStream_t s) {
   const unsigned tiles = (unsigned)((p.n + kC9TilePoints - 1) / kC9TilePoints);
-  const dim3 grid(tiles, (unsigned)((p.F + kC9Frames - 1) / kC9Frames));
+  const dim3 grid(tiles, (unsigned)((p.F + kZ9Frames - 1) / kZ9Frames));
   REQUIRE(grid.y <= 65535u, "too many frames in one call");
   CullTilePrep* prep = nullptr;
   keep_workspace_pool();
@@ -873,13 +866,7 @@ static int launch_zbuf9(const FrameLoopParams& p, int dt, cudaStream_t s) {
   c.depth_stride = p.depth_stride, c.K = p.K, c.g = p.g;
   q.prep = prep;
   const float fdw = (float)p.g.depth_w, fdh = (float)p.g.depth_h;
-  auto dup = [](float v) {
-    uint32_t b;
-    memcpy(&b, &v, 4);
-    return (unsigned long long)b | ((unsigned long long)b << 32);
-  };
-  q.nfdw2 = dup(-fdw), q.nfdh2 = dup(-fdh), q.fdw2 = dup(fdw);
-  q.magic2 = dup(12582912.0f), q.two23_2 = dup(8388608.0f), q.ntwo23_2 = dup(-8388608.0f);
+  q.nfdw = -fdw, q.nfdh = -fdh, q.fdw = fdw, q.fscale = (float)p.g.depth_scale;
   q.xclip = (fdw - 1.0f) + 8388608.0f, q.yclip = fdh - 1.0f;
   constexpr int smem = (int)offsetof(CullTilePrep, pt_slot);
   switch (dt) {
