@@ -17,3 +17,4 @@ compute-sanitizer --tool memcheck python __graft_entry__.py smoke > gpurun_out/r
 compute-sanitizer --tool racecheck python __graft_entry__.py smoke > gpurun_out/r2_sanitizer_racecheck_smoke.log 2>&1
 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_configs.py -m gpu -x -q > gpurun_out/r2_sanitizer_memcheck_pytest.log 2>&1
 for f in gpurun_out/r2_sanitizer_*.log; do tail -n 3 "$f"; done
+TB_STREAM_ONLY=1 python profiles/table_bench.py > gpurun_out/r2_tables_stream.json 2> gpurun_out/r2_tables_stream.err; cat gpurun_out/r2_tables_stream.json

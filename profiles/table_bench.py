@@ -133,7 +133,12 @@ def stream_scenes(writers, n_scenes=8):
 
 
 stream_scenes(1, 2)
-out["visibility_stream_frames_per_s"] = {"single_file_1_writer": stream_scenes(1)[0], "dataset_8_writers": stream_scenes(8)[0]}
+out["visibility_stream_frames_per_s"] = {"single_file_1_writer": stream_scenes(1)[0], "dataset_8_writers": stream_scenes(8)[0],
+                                         "dataset_8_writers_24_scenes": stream_scenes(8, 24)[0],
+                                         "dataset_16_writers_32_scenes": stream_scenes(16, 32)[0]}
+if os.environ.get("TB_STREAM_ONLY"):
+    print(json.dumps(out))
+    sys.exit(0)
 
 # ---- dict path (GPU geometry, Python formatting) — what this repo did before the device formatter
 def dict_visibility():
