@@ -170,7 +170,11 @@ def test_fused_object_counts_mixed_groups_and_fallback():
     runs255 = np.repeat(rng.integers(0, 256, 2000), rng.integers(5, 130, 2000))[:s.n_points].astype(np.uint16)
     runs2000 = np.repeat(rng.integers(0, 2001, 9000), rng.integers(1, 20, 9000))
     runs2000 = np.resize(runs2000, s.n_points).astype(np.uint16)
-    for n_obj, ids in ((9, s.instance_ids.copy()), (40, rng.integers(0, 45, s.n_points).astype(np.uint16)),
+    # few objects in short runs: every 64-point super-group carries 3-5 ids that all fit the tile's 15-entry table (the
+    # per-lane `match_any` path of msp_cull9.cuh without its global-atomic overflow)
+    runs20 = np.resize(np.repeat(np.arange(9), 20), s.n_points).astype(np.uint16)
+    runs27 = np.resize(np.repeat(rng.integers(0, 9, 5000), 27), s.n_points).astype(np.uint16)
+    for n_obj, ids in ((9, s.instance_ids.copy()), (8, runs20), (8, runs27), (40, rng.integers(0, 45, s.n_points).astype(np.uint16)),
                        (100, rng.integers(0, 101, s.n_points).astype(np.uint16)), (255, runs255), (2000, runs2000)):
         ids[::977] = 60000                                  # out-of-range ids are ignored (treated as "no object")
         sc = DeviceScene(s.points, s.K, s.c2w, axis_align=s.axis_align, instance_ids=ids, num_objects=n_obj)
