@@ -31,8 +31,8 @@ if ROOT not in sys.path:
 METRIC = "annotated_frame_pairs_per_sec"
 UNIT = "pairs/s"
 DEPTH_BYTES = 640 * 480 * 2
-TILE_POINTS = 2048            # msp_cull9.cuh: kC9TilePoints
-TILE_PREP_BYTES = 27744       # sizeof(CullTilePrep)
+TILE_POINTS = 1024            # msp_cull9.cuh: kC9TilePoints
+TILE_PREP_BYTES = 13904       # sizeof(CullTilePrep)
 
 
 def algorithmic_bytes_frame(n: int) -> float:
@@ -458,22 +458,23 @@ def main_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = comp_bytes / (k1_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_note = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        _tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        traffic, traffic_note = _tr.get("dram_bytes_per_launch"), _tr.get("note")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_frame_cull9 (+ k_cull_prepare) = msp_project_visibility_objects", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": traffic, "compulsory_bytes_per_launch": comp_bytes / k1_launches,
+                "traffic": traffic, "traffic_note": traffic_note, "compulsory_bytes_per_launch": comp_bytes / k1_launches,
                 "avg_launch_ms": k1_ms / k1_launches, "share_of_step": k1_ms / elapsed_local,
                 "bytes_model": ("compulsory HBM bytes WITH the kernel's reuse: depth maps + mask words + counts + points in + prepared "
                                 "tiles out/in + poses, each once per launch (bench.py compulsory_bytes_launch)"),
                 "algorithmic_bytes_per_launch": alg_bytes / k1_launches,
                 "algorithmic_frac": alg_bytes / (k1_ms * 1e-3) / 1e9 / peak,
                 "algorithmic_note": ("SURVEY.md §8(d)'s independent-pair bytes (every frame streams the scene's points: 12N + 614400 + 80 + "
-                                     "N/8).  NOT a physical fraction: the kernel stages each 2048-point tile once per 32-frame chunk and "
+                                     "N/8).  NOT a physical fraction: the kernel stages each 1024-point tile once per 32-frame chunk and "
                                      "re-reads come from L2, so this ratio can exceed 1; `frac` is the physical one")}
     if traffic:
         dram_gbs = traffic / (k1_ms / k1_launches * 1e-3) / 1e9

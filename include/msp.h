@@ -104,7 +104,7 @@ MSP_API int msp_project_visibility(const void* pts, int64_t n, int32_t pts_dtype
                            int64_t mask_stride_words, double* xy_out, double* z_out, void* stream);
 
 /* msp_project_visibility fused with msp_object_counts (COV:110-136): the masks AND counts[f*n_objects + o] in one
- * pass over the points, for any number of objects (each 2048-point tile keeps a table of its own instance ids; falls
+ * pass over the points, for any number of objects (each 1024-point tile keeps a table of its own instance ids; falls
  * back to the two separate kernels only when the intrinsics are not the standard form or n_objects == 0).
  * counts (F,n_objects) is overwritten.  Both visibility entry points use a stream-ordered workspace
  * (cudaMallocAsync / cudaFreeAsync on `stream`, ~14 KB per 1000 points) for the prepared point tiles. */

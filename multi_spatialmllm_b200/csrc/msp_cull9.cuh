@@ -8,7 +8,7 @@
 //
 //   * k_cull_prepare (one launch per call, ~2 % of K1's time) does everything that only depends on the POINTS once instead
 //     of once per (tile, frame chunk): tile centre, re-centred float32 coordinates, super-group boxes, extents and the
-//     per-tile instance-id table.  Its output (CullTilePrep, 27 KB per 2 048-point tile) is what the main kernel stages
+//     per-tile instance-id table.  Its output (CullTilePrep, 13.6 KB per 1 024-point tile) is what the main kernel stages
 //     into shared memory with ONE bulk async copy (TMA engine, UBLKCP) — no reductions, no re-centring in the hot kernel.
 //   * the unit of evaluation is a SUPER-GROUP of 64 consecutive points, two per lane, stored as float2 (lo, hi): the whole
 //     float32 projection runs on Blackwell's packed FFMA2 / FADD2 / FMUL2 (fma.rn.f32x2 ...), which take one issue slot
@@ -25,7 +25,7 @@
 //   * uncertain lanes are queued per warp ACROSS frames and the exact float64 path runs on 32 of them at a time, OR-ing
 //     visible bits into the stored words (the validated round-1 "deferred exact" variant, now the only exact path — a
 //     non-standard frame simply queues every lane and becomes the all-float64 kernel at full lane utilisation);
-//   * fused per-(frame, object) counting works for ANY number of objects: a tile of 2 048 consecutive points touches few
+//   * fused per-(frame, object) counting works for ANY number of objects: a tile of 1 024 consecutive points touches few
 //     instances, so the prepare pass gives each tile a 15-entry table of its ids and marks every super-group whose points
 //     share one id; such a super-group adds its popcount to counts[frame][id] with ONE global RED per frame (no shared
 //     histogram, no end-of-CTA barrier), mixed ones aggregate by id within the warp first; ids that do not fit the table
@@ -44,12 +44,15 @@
 
 namespace msp {
 
-constexpr int kC9Threads = 256;
+#ifndef MSP_C9_THREADS
+#define MSP_C9_THREADS 128     // 4 warps, 1 024-point tiles, 8 CTAs/SM: same warps per SM as 256 x 4 but finer-grained CTAs (0.373 -> 0.362 ms)
+#endif
+constexpr int kC9Threads = MSP_C9_THREADS;
 constexpr int kC9Warps = kC9Threads / 32;
 constexpr int kC9SgPerWarp = 4;                                   // super-groups (64 points, two per lane) per warp
-constexpr int kC9TileSgs = kC9Warps * kC9SgPerWarp;               // 32
-constexpr int kC9TilePoints = kC9TileSgs * 64;                    // 2048
-constexpr int kC9TileWords = kC9TilePoints / 32;                  // 64 mask words per tile and frame
+constexpr int kC9TileSgs = kC9Warps * kC9SgPerWarp;               // 16
+constexpr int kC9TilePoints = kC9TileSgs * 64;                    // 1024
+constexpr int kC9TileWords = kC9TilePoints / 32;                  // 32 mask words per tile and frame
 #ifndef MSP_C9_FRAMES
 #define MSP_C9_FRAMES 32
 #endif
@@ -58,7 +61,7 @@ constexpr int kC9Rounds = kC9Frames / 32;
 static_assert(kC9Frames % 32 == 0 && kC9Frames <= 256, "frames per CTA");
 constexpr int kC9Slots = 16;                                      // local instance-id slots per tile (slot 15 is never used: 15 ids)
 #ifndef MSP_C9_MINBLOCKS
-#define MSP_C9_MINBLOCKS 4
+#define MSP_C9_MINBLOCKS (1024 / MSP_C9_THREADS)   // 32 warps per SM at 64 registers
 #endif
 #ifndef MSP_C9_STRIDED
 #define MSP_C9_STRIDED 1       // 1: warp w owns super-groups w, w+8, w+16, w+24 (even work per warp), 0: 4w .. 4w+3
@@ -149,7 +152,7 @@ __device__ __forceinline__ void lds128(uint32_t addr, f32x2& a, f32x2& b) {
 }
 
 // ================================================================================================================
-// prepare pass: everything that depends on the points only.  One CTA per 2 048-point tile, warp w owns super-groups 4w..4w+3.
+// prepare pass: everything that depends on the points only.  One CTA per 1 024-point tile, warp w owns super-groups 4w..4w+3.
 // ================================================================================================================
 template <int DT>
 __global__ void __launch_bounds__(kC9Threads) k_cull_prepare(const void* __restrict__ pts, int64_t n,
