@@ -479,7 +479,8 @@ def main_gpu(args):
     if traffic:
         dram_gbs = traffic / (k1_ms / k1_launches * 1e-3) / 1e9
         roofline.update(dram_gbs=dram_gbs, dram_frac=dram_gbs / peak,
-                        traffic_note="ncu dram__bytes_read+write of one launch on a 200k-point x 2000-frame scene (profiles/k1_traffic.json)")
+                        traffic_note="ncu dram__bytes_read+write of one launch on a 200k-point x 2000-frame scene (profiles/k1_traffic.json)"
+                                     + ("; " + traffic_note if traffic_note else ""))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
