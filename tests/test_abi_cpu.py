@@ -81,3 +81,23 @@ def test_package_command_table_cpu(capsys):
     with pytest.raises(SystemExit) as e:                      # argparse --help of a dispatched command exits 0
         cli.main(["visual_correspondence_qa_engine_coor_2_coor.py", "--help"])
     assert e.value.code == 0
+
+
+def test_bench_byte_model_follows_the_kernel_tile_size():
+    """bench.py's compulsory-bytes model (roofline.frac) uses the tile size and the prepared-tile record size of
+    msp_cull9.cuh; keep them in step with the header (CullTilePrep: re-centred points, boxes, header, id table, point slots)."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "multi_spatialmllm_b200", "csrc", "msp_cull9.cuh")).read()
+    threads = int(re.search(r"#define MSP_C9_THREADS (\d+)", src).group(1))
+    sg_per_warp = int(re.search(r"constexpr int kC9SgPerWarp = (\d+);", src).group(1))
+    slots = int(re.search(r"constexpr int kC9Slots = (\d+);", src).group(1))
+    sgs = threads // 32 * sg_per_warp
+    points = sgs * 64
+    prep = sgs * 3 * 32 * 8 + sgs * 2 * 16 + (3 + 3 + 2) * 4 + slots * 2 + sgs + points
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.TILE_POINTS == points
+    assert bench.TILE_PREP_BYTES == prep and prep % 16 == 0
