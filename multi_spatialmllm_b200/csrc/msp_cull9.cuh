@@ -64,7 +64,7 @@ constexpr int kC9Slots = 16;                                      // local insta
 #define MSP_C9_MINBLOCKS (1024 / MSP_C9_THREADS)   // 32 warps per SM at 64 registers
 #endif
 #ifndef MSP_C9_STRIDED
-#define MSP_C9_STRIDED 1       // 1: warp w owns super-groups w, w+8, w+16, w+24 (even work per warp), 0: 4w .. 4w+3
+#define MSP_C9_STRIDED 1       // 1: warp w owns super-groups w, w+W, w+2W, w+3W for W warps per CTA (even work per warp), 0: 4w .. 4w+3
 #endif
 #ifndef MSP_C9_COEF_PER_SG
 #define MSP_C9_COEF_PER_SG 1   // 1: the 12 frame coefficients are re-read from shared memory for every super-group (fewer live registers
